@@ -1,0 +1,185 @@
+/* simplediffeq_cuda.h -- C ABI of libsimplediffeq_cuda (B200 / sm_100a ensemble ODE integrator).
+ *
+ * Drop-in boundary for the GPU solver family of SciML/SimpleDiffEq.jl v1.16.3.  One call solves a
+ * whole ensemble; each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository):
+ *
+ *   sde_solve / sde_solve_device
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleTsit5;  saveat, save_everystep, dt)                 src/tsit5/gpuatsit5.jl:55-147
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleATsit5; dt, saveat, save_everystep, abstol, reltol) src/tsit5/gpuatsit5.jl:205-336
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleRK4;    dt)                                         src/rk4/gpurk4.jl:53-98
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleVern7 / GPUSimpleAVern7; ...)                       src/verner/gpuvern7.jl:55-242, :300-536
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleVern9 / GPUSimpleAVern9; ...)                       src/verner/gpuvern9.jl:55-353, :411-779
+ *     called once per trajectory by SciMLBase's ensemble driver (batch_func) in the reference; here
+ *     ALL trajectories of `solve(EnsembleProblem(prob; prob_func), alg; trajectories, ...)` cross the
+ *     boundary in one call.
+ *   sde_system_builtin / sde_system_nvrtc
+ *       `prob.f` (an arbitrary Julia callable f(u,p,t) in the reference, src/tsit5/gpuatsit5.jl:65):
+ *       a built-in registry entry or a CUDA-C `__device__` function JIT-compiled with NVRTC.
+ *   per-trajectory retcode
+ *       the reference's exceptions: error("dt<dtmin") src/tsit5/gpuatsit5.jl:256,
+ *       src/verner/gpuvern7.jl:358, src/verner/gpuvern9.jl:466; ReturnCode.Default otherwise
+ *       (test/gpu_ode_regression.jl:24-25).
+ *
+ * All functions return SDE_OK (0) or a negative error code; sde_last_error() gives the message of
+ * the calling thread's last failure.  Nothing throws across this boundary.  The library is
+ * re-entrant; system handles may be shared between threads.
+ */
+#ifndef SIMPLEDIFFEQ_CUDA_H
+#define SIMPLEDIFFEQ_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDE_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define SDE_API __attribute__((visibility("default")))
+#else
+#define SDE_API
+#endif
+
+/* status codes */
+enum {
+  SDE_OK = 0,
+  SDE_ERR_INVALID = -1,     /* bad argument */
+  SDE_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+  SDE_ERR_NVRTC = -3,       /* user RHS failed to compile */
+  SDE_ERR_UNSUPPORTED = -4, /* combination not provided by this build */
+  SDE_ERR_NOMEM = -5
+};
+
+/* algorithms (the reference's GPUSimple* singletons) */
+enum {
+  SDE_ALG_TSIT5 = 0,  /* GPUSimpleTsit5   fixed step  */
+  SDE_ALG_ATSIT5 = 1, /* GPUSimpleATsit5  adaptive    */
+  SDE_ALG_RK4 = 2,    /* GPUSimpleRK4     fixed step, always saves every step in the reference */
+  SDE_ALG_VERN7 = 3,  /* GPUSimpleVern7   fixed step  */
+  SDE_ALG_AVERN7 = 4, /* GPUSimpleAVern7  adaptive    */
+  SDE_ALG_VERN9 = 5,  /* GPUSimpleVern9   fixed step  */
+  SDE_ALG_AVERN9 = 6  /* GPUSimpleAVern9  adaptive    */
+};
+
+enum { SDE_F64 = 0, SDE_F32 = 1 };
+
+/* what is saved */
+enum {
+  SDE_SAVE_ENDPOINT = 0,  /* saveat === nothing && save_everystep = false : final state only */
+  SDE_SAVE_SAVEAT = 1,    /* saveat = [...] : dense output at the given times */
+  SDE_SAVE_EVERYSTEP = 2  /* saveat === nothing && save_everystep = true (fixed-step algorithms):
+                             n_steps + 1 states, slot 0 = u0 */
+};
+
+/* layout of series outputs (SAVEAT / EVERYSTEP); n_out = slots per trajectory */
+enum {
+  SDE_LAYOUT_TRAJ_MAJOR = 0, /* out_u[(i*n_out + s)*n_state + c] : per-trajectory Vector{SVector} */
+  SDE_LAYOUT_SOA = 1         /* out_u[(s*n_state + c)*n_traj + i] : coalesced, trajectory fastest */
+};
+
+/* per-trajectory return codes */
+enum {
+  SDE_RET_DEFAULT = 0,  /* ReturnCode.Default */
+  SDE_RET_DTMIN = 1,    /* the reference would throw error("dt<dtmin") */
+  SDE_RET_MAXITERS = 2  /* max_attempts exhausted (no counterpart in the reference) */
+};
+
+/* compat flags: 0 = reproduce the reference exactly, including its quirks */
+enum {
+  SDE_COMPAT_FIX_VERN9_INTERP = 1 /* fixed-step GPUSimpleVern9 + saveat: use stages 8..15 in the dense
+                                     output (the reference uses k2..k9, src/verner/gpuvern9.jl:216-331) */
+};
+
+typedef struct sde_system_s* sde_system_t;
+
+typedef struct sde_options {
+  int32_t alg;        /* SDE_ALG_* */
+  int32_t dtype;      /* SDE_F64 / SDE_F32: element type of every buffer and of all arithmetic */
+  int32_t save_mode;  /* SDE_SAVE_* */
+  int32_t layout;     /* SDE_LAYOUT_* (series outputs) */
+  int32_t compat;     /* SDE_COMPAT_* flags */
+  int32_t reserved;
+  int64_t n_traj;     /* `trajectories` */
+  double t0, tf;      /* prob.tspan (converted to dtype) */
+  double dt;          /* dt (fixed step) / initial dt (adaptive); reference default 0.1f0 */
+  double abstol;      /* adaptive; reference default 1f-6 */
+  double reltol;      /* adaptive; reference default 1f-3 */
+  int64_t n_steps;    /* fixed step: length(t0:dt:tf) - 1 */
+  const void* tgrid;  /* fixed step: HOST array, the n_steps+1 elements of t0:dt:tf in dtype.
+                         May be NULL: then t0 + k*dt (rounded product, rounded sum) is used. */
+  const void* saveat; /* SDE_SAVE_SAVEAT: HOST array of n_save times in dtype */
+  int64_t n_save;
+  int64_t max_attempts; /* adaptive: 0 = unlimited like the reference */
+} sde_options_t;
+
+/* ---- library / device ------------------------------------------------------------------- */
+SDE_API int sde_version(void);
+SDE_API const char* sde_last_error(void);
+SDE_API int sde_device_count(int* count);
+
+/* ---- right-hand sides --------------------------------------------------------------------- */
+/* names: "lorenz", "vanderpol", "robertson", "nbody", "lineardecay", "scalargrowth",
+ * "nonautonomous".  Handles of built-ins are static; sde_system_free on them is a no-op. */
+SDE_API int sde_system_builtin(const char* name, sde_system_t* out);
+
+/* User RHS.  `src` is CUDA C++ defining
+ *     __device__ void rhs(real* du, const real* u, const real* p, real t)
+ * (`real` is typedef'd to double or float by the library).  It is compiled for sm_100a with
+ * --fmad=false so that the user's arithmetic rounds as written (the reference does not fuse f).
+ * Kernels are compiled lazily per (algorithm, dtype, save mode) and cached in the handle.
+ * `log`/`log_len`: optional buffer receiving the NVRTC log of a failed compile of the syntax
+ * check done here. */
+SDE_API int sde_system_nvrtc(const char* src, int n_state, int n_param, sde_system_t* out, char* log,
+                     size_t log_len);
+SDE_API int sde_system_dims(sde_system_t sys, int* n_state, int* n_param);
+SDE_API void sde_system_free(sde_system_t sys);
+/* Compile (without launching) the kernel a solve with these options would use.  Works without a
+ * GPU for NVRTC systems; for built-ins it only checks that the kernel exists in this build. */
+SDE_API int sde_system_prepare(sde_system_t sys, const sde_options_t* opt);
+
+/* ---- solve, host buffers ------------------------------------------------------------------ */
+/* u0: [n_state][n_traj] (SoA), p: [n_param][n_traj] (SoA), HOST memory (pinned or pageable).
+ * out_u: ENDPOINT -> [n_state][n_traj] (SoA final states)
+ *        SAVEAT   -> n_out = n_save slots per trajectory, layout per opt->layout
+ *        EVERYSTEP-> n_out = n_steps + 1 slots per trajectory
+ *        series slots that the reference would leave `undef` are NaN.
+ * out_t: adaptive: [n_traj] final time of each trajectory (== tf unless retcode != 0); may be NULL.
+ *        fixed step: ignored (times are trajectory independent: see sde_fixed_times).
+ * naccept/nreject/retcode: [n_traj] int32, each may be NULL.
+ * devices/n_dev: CUDA device ordinals to shard over by contiguous trajectory ranges, one host
+ *        thread + stream per device, no collective; NULL/0 = current device only. */
+SDE_API int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const void* p,
+              void* out_u, void* out_t, int32_t* naccept, int32_t* nreject, int32_t* retcode,
+              const int* devices, int n_dev);
+
+/* ---- solve, device-resident buffers ------------------------------------------------------- */
+/* Same contract with DEVICE pointers on the current device; opt->tgrid / opt->saveat remain HOST
+ * arrays (small; uploaded and cached per call).  `ld_in` / `ld_out` are the component strides of the
+ * SoA inputs / endpoint (or SoA series) outputs, so that a shard of a larger array can be solved
+ * in place (pass n_traj = shard length, pointers offset to the shard start).  Work is enqueued
+ * on `stream` (a cudaStream_t, NULL = default stream) and the call returns without
+ * synchronising when `async` != 0. */
+SDE_API int sde_solve_device(sde_system_t sys, const sde_options_t* opt, const void* d_u0, const void* d_p,
+                     int64_t ld_in, void* d_out_u, int64_t ld_out, void* d_out_t,
+                     int32_t* d_naccept, int32_t* d_nreject, int32_t* d_retcode, void* stream,
+                     int async);
+
+/* Times the reference would put in sol.t for a fixed-step solve (identical for every trajectory):
+ * ENDPOINT -> 2 values [t0, t_end]; EVERYSTEP -> n_steps+1 values; SAVEAT -> copy of saveat.
+ * `out` is a HOST array in dtype with room for `n` values; returns the count written in *n_written. */
+SDE_API int sde_fixed_times(const sde_options_t* opt, void* out, int64_t n, int64_t* n_written);
+
+/* Pinned host memory helpers (so that the H2D/D2H copies of sde_solve run at full PCIe rate). */
+SDE_API int sde_host_alloc(void** ptr, size_t bytes);
+SDE_API int sde_host_free(void* ptr);
+
+/* Number of kernels launched by this process through the library (all threads). */
+SDE_API int64_t sde_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLEDIFFEQ_CUDA_H */

@@ -1,0 +1,925 @@
+// oracle/oracle.cpp -- CPU restatement of SimpleDiffEq.jl's GPUSimple* solve bodies.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference leg may load this library; nothing under
+// simplediffeq.jl_b200/ links, imports or calls it.
+//
+// PARITY STATUS: "parity unpinned" at the bit level.  The reference (pure Julia, v1.16.3)
+// ships no golden vectors / known-answer files for this path and Julia is not available in
+// the build container, so the reference itself could not be executed.  The restatement is
+// pinned only by (a) the reference's own tolerance tests restated in tests/
+// (test/gpu_ode_regression.jl, test/gpusimpleatsit5_tests.jl), (b) convergence-order and
+// interpolant-identity checks, (c) mpmath high-precision solutions.  Every function cites
+// the reference file:line it follows (paths relative to SciML/SimpleDiffEq.jl).
+//
+// Third-party arithmetic the reference relies on and that is restated here from the
+// published behaviour (assumptions A1-A9):
+//   MuladdMacro.@muladd (>=0.2.4): `x + a*b + c*d` -> muladd(c,d, muladd(a,b,x)); all-product
+//     sums fold left starting from the first product; `dt*a21*k1` splits as (dt*a21)*k1;
+//     dotted/undotted mixes are not fused.  muladd == hardware FMA (x86-64 with FMA).
+//   StaticArrays: element-wise muladd / + / * on SVector; sum(abs2, v) is a left fold.
+//   DiffEqBase.ODE_DEFAULT_NORM(SVector, t) = sqrt(sum(abs2,u)/length(u)); scalar -> abs.
+//   Base.@evalpoly = Horner with muladd.  Base min/max propagate NaN; FastMath min/max are
+//     ifelse(y > x, ...) forms.  `@fastmath x^y` = libm-class pow (never bit-reproducible).
+//
+// Build: g++ -O2 -std=c++17 -mfma -ffp-contract=off -fPIC -shared -pthread oracle.cpp -o liboracle.so
+//   -ffp-contract=off is REQUIRED: only the explicit std::fma calls may fuse.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "tableau_named.hpp"
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// tiny static vector with the element-wise operations StaticArrays provides
+// ------------------------------------------------------------------------------------
+template <class T, int N>
+struct Vec {
+  T v[N];
+  T& operator[](int i) { return v[i]; }
+  const T& operator[](int i) const { return v[i]; }
+};
+
+template <class T> inline T fmaT(T a, T b, T c) { return std::fma(a, b, c); }
+
+// muladd(a::Number, k::SVector, c::SVector)
+template <class T, int N>
+inline Vec<T, N> muladd(T a, const Vec<T, N>& k, const Vec<T, N>& c) {
+  Vec<T, N> r;
+  for (int i = 0; i < N; ++i) r[i] = fmaT(a, k[i], c[i]);
+  return r;
+}
+template <class T, int N>
+inline Vec<T, N> mul(T a, const Vec<T, N>& k) {
+  Vec<T, N> r;
+  for (int i = 0; i < N; ++i) r[i] = a * k[i];
+  return r;
+}
+template <class T, int N>
+inline Vec<T, N> add(const Vec<T, N>& a, const Vec<T, N>& b) {
+  Vec<T, N> r;
+  for (int i = 0; i < N; ++i) r[i] = a[i] + b[i];
+  return r;
+}
+
+// @muladd of an all-products sum  a1*k1 + a2*k2 + ... :  muladd(an,kn, ... muladd(a2,k2, a1*k1))
+template <class T, int N>
+inline Vec<T, N> msum(T a1, const Vec<T, N>& k1) { return mul(a1, k1); }
+template <class T, int N, class... Rest>
+inline Vec<T, N> msum_acc(const Vec<T, N>& acc) { return acc; }
+template <class T, int N, class... Rest>
+inline Vec<T, N> msum_acc(const Vec<T, N>& acc, T a, const Vec<T, N>& k, Rest... rest) {
+  return msum_acc<T, N>(muladd(a, k, acc), rest...);
+}
+template <class T, int N, class... Rest>
+inline Vec<T, N> msum(T a1, const Vec<T, N>& k1, T a2, const Vec<T, N>& k2, Rest... rest) {
+  return msum_acc<T, N>(muladd(a2, k2, mul(a1, k1)), rest...);
+}
+
+// Julia Base.min / Base.max: NaN-propagating
+template <class T> inline T jl_min(T a, T b) { return (a != a || b != b) ? std::numeric_limits<T>::quiet_NaN() : (b < a ? b : a); }
+template <class T> inline T jl_max(T a, T b) { return (a != a || b != b) ? std::numeric_limits<T>::quiet_NaN() : (b > a ? b : a); }
+// Base.FastMath.min_fast / max_fast
+template <class T> inline T min_fast(T x, T y) { return (y > x) ? x : y; }
+template <class T> inline T max_fast(T x, T y) { return (y > x) ? y : x; }
+
+// @evalpoly(x, c0, c1, ..., cn): Horner with muladd
+template <class T>
+inline T evalpoly(T x, std::initializer_list<T> c) {
+  const T* b = c.begin();
+  int n = (int)c.size();
+  T acc = b[n - 1];
+  for (int i = n - 2; i >= 0; --i) acc = fmaT(x, acc, b[i]);
+  return acc;
+}
+
+// DiffEqBase.ODE_DEFAULT_NORM(u::SArray, t) = sqrt(sum(abs2,u)/length(u)); scalar state -> abs(u)
+template <class T, int N>
+inline T ode_default_norm(const Vec<T, N>& u) {
+  if (N == 1) return std::fabs(u[0]);
+  T s = u[0] * u[0];
+  for (int i = 1; i < N; ++i) s = s + u[i] * u[i];
+  return std::sqrt(s / T(N));
+}
+
+// ------------------------------------------------------------------------------------
+// right-hand sides.  Lorenz / linear decay / scalar growth are the reference's test and
+// docstring functions; the others have NO reference definition and are
+// defined by this project (formula and operation order in DESIGN.md; the CUDA registry
+// sde_systems.cuh restates the same order).  User RHS are NOT fused (no @muladd there).
+// ------------------------------------------------------------------------------------
+struct Lorenz {  // test/gpusimpleatsit5_tests.jl:3-13
+  static constexpr int N = 3, NP = 3;
+  template <class T> static Vec<T, 3> f(const Vec<T, 3>& u, const T* p, T) {
+    Vec<T, 3> du;
+    du[0] = p[0] * (u[1] - u[0]);
+    du[1] = u[0] * (p[1] - u[2]) - u[1];
+    du[2] = u[0] * u[1] - p[2] * u[2];
+    return du;
+  }
+};
+struct VanDerPol {  // (u2, p1*(1-u1*u1)*u2 - u1)
+  static constexpr int N = 2, NP = 1;
+  template <class T> static Vec<T, 2> f(const Vec<T, 2>& u, const T* p, T) {
+    Vec<T, 2> du;
+    du[0] = u[1];
+    du[1] = (p[0] * (T(1) - u[0] * u[0])) * u[1] - u[0];
+    return du;
+  }
+};
+struct Robertson {  // du1 = -p1*u1 + p3*u2*u3; du2 = p1*u1 - p2*u2*u2 - p3*u2*u3; du3 = p2*u2*u2
+  static constexpr int N = 3, NP = 3;
+  template <class T> static Vec<T, 3> f(const Vec<T, 3>& u, const T* p, T) {
+    Vec<T, 3> du;
+    du[0] = (-p[0]) * u[0] + (p[2] * u[1]) * u[2];
+    du[1] = (p[0] * u[0] - (p[1] * u[1]) * u[1]) - (p[2] * u[1]) * u[2];
+    du[2] = (p[1] * u[1]) * u[1];
+    return du;
+  }
+};
+struct NBodyLite {  // 3 planar bodies, G = 1, masses p1..p3, Plummer softening eps^2 = 1e-4 (as T)
+  // state (x1,y1,x2,y2,x3,y3,vx1,vy1,vx2,vy2,vx3,vy3)
+  static constexpr int N = 12, NP = 3;
+  template <class T> static Vec<T, 12> f(const Vec<T, 12>& u, const T* p, T) {
+    Vec<T, 12> du;
+    for (int i = 0; i < 6; ++i) du[i] = u[6 + i];
+    const T eps2 = T(1.0e-4);
+    T ax[3] = {T(0), T(0), T(0)}, ay[3] = {T(0), T(0), T(0)};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        if (a == b) continue;
+        T dx = u[2 * b] - u[2 * a];
+        T dy = u[2 * b + 1] - u[2 * a + 1];
+        T r2 = (dx * dx + dy * dy) + eps2;
+        T w = p[b] / (r2 * std::sqrt(r2));
+        ax[a] = ax[a] + w * dx;
+        ay[a] = ay[a] + w * dy;
+      }
+    for (int a = 0; a < 3; ++a) { du[6 + 2 * a] = ax[a]; du[7 + 2 * a] = ay[a]; }
+    return du;
+  }
+};
+struct LinearDecay {  // test/gpu_ode_regression.jl:2-4: f(u,p,t) = -u
+  static constexpr int N = 3, NP = 3;
+  template <class T> static Vec<T, 3> f(const Vec<T, 3>& u, const T*, T) {
+    Vec<T, 3> du;
+    for (int i = 0; i < 3; ++i) du[i] = -u[i];
+    return du;
+  }
+};
+struct ScalarGrowth {  // docstrings (gpuatsit5.jl:33): f(u,p,t) = 1.01*u, here p1*u, scalar state
+  static constexpr int N = 1, NP = 1;
+  template <class T> static Vec<T, 1> f(const Vec<T, 1>& u, const T* p, T) {
+    Vec<T, 1> du;
+    du[0] = p[0] * u[0];
+    return du;
+  }
+};
+struct NonAutonomous {  // time-dependent test system: du1 = u2 + t; du2 = -p1*u1 + p2*t*t
+  static constexpr int N = 2, NP = 2;
+  template <class T> static Vec<T, 2> f(const Vec<T, 2>& u, const T* p, T t) {
+    Vec<T, 2> du;
+    du[0] = u[1] + t;
+    du[1] = (-p[0]) * u[0] + (p[1] * t) * t;
+    return du;
+  }
+};
+// user RHS compiled by the test harness with g++ from the same source string NVRTC gets
+typedef void (*user_rhs_f64)(double* du, const double* u, const double* p, double t);
+typedef void (*user_rhs_f32)(float* du, const float* u, const float* p, float t);
+template <int NN>
+struct UserSys {
+  static constexpr int N = NN, NP = 8;  // NP = capacity; the runtime count is EnsembleArgs::n_param
+  static thread_local void* fn;
+  template <class T> static Vec<T, NN> f(const Vec<T, NN>& u, const T* p, T t) {
+    Vec<T, NN> du;
+    if (sizeof(T) == 8) ((user_rhs_f64)fn)((double*)du.v, (const double*)u.v, (const double*)p, (double)t);
+    else ((user_rhs_f32)fn)((float*)du.v, (const float*)u.v, (const float*)p, (float)t);
+    return du;
+  }
+};
+template <int NN> thread_local void* UserSys<NN>::fn = nullptr;
+
+// ------------------------------------------------------------------------------------
+// per-trajectory job description
+// ------------------------------------------------------------------------------------
+enum { SAVE_ENDPOINT = 0, SAVE_SAVEAT = 1, SAVE_EVERYSTEP = 2 };
+enum { ALG_TSIT5 = 0, ALG_ATSIT5 = 1, ALG_RK4 = 2, ALG_VERN7 = 3, ALG_AVERN7 = 4, ALG_VERN9 = 5, ALG_AVERN9 = 6 };
+enum { RET_DEFAULT = 0, RET_DTMIN = 1, RET_MAXITERS = 2 };
+enum { COMPAT_FIX_VERN9_INTERP = 1 };
+
+template <class T>
+struct Job {
+  T t0, tf, dt, abstol, reltol;
+  int64_t n_steps;     // fixed step: length(t0:dt:tf) - 1
+  const T* tgrid;      // fixed step: the n_steps+1 elements of t0:dt:tf
+  const T* saveat;     // or null
+  int64_t n_save;
+  int save_mode;
+  int compat;
+  int64_t max_out;     // capacity (slots) of the per-trajectory output
+  int64_t max_attempts;  // 0 = unlimited (reference has no maxiters)
+};
+
+template <class T, int N>
+struct Out {
+  T* u;          // [max_out][N]
+  T* t;          // [max_out] or null
+  int64_t n;     // slots written
+  int32_t naccept, nreject, retcode;
+  void put(int64_t slot, const Vec<T, N>& x, T tt, int64_t cap) {
+    if (slot < cap) {
+      for (int i = 0; i < N; ++i) u[slot * N + i] = x[i];
+      if (t) t[slot] = tt;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// Tsit5 pieces
+// ------------------------------------------------------------------------------------
+template <class T> using TS = oracle_tab::Tsit5Tab<T>;
+
+// src/tsit5/tsit5.jl:385-399
+template <class T>
+inline void tsit5_bthetas(T th, T (&b)[7]) {
+  const T z = T(0);
+  b[0] = evalpoly<T>(th, {z, TS<T>::r11, TS<T>::r12, TS<T>::r13, TS<T>::r14});
+  b[1] = evalpoly<T>(th, {z, z, TS<T>::r22, TS<T>::r23, TS<T>::r24});
+  b[2] = evalpoly<T>(th, {z, z, TS<T>::r32, TS<T>::r33, TS<T>::r34});
+  b[3] = evalpoly<T>(th, {z, z, TS<T>::r42, TS<T>::r43, TS<T>::r44});
+  b[4] = evalpoly<T>(th, {z, z, TS<T>::r52, TS<T>::r53, TS<T>::r54});
+  b[5] = evalpoly<T>(th, {z, z, TS<T>::r62, TS<T>::r63, TS<T>::r64});
+  b[6] = evalpoly<T>(th, {z, z, TS<T>::r72, TS<T>::r73, TS<T>::r74});
+}
+
+// the six stages + update shared by gpuatsit5.jl:99-110 and :258-270
+template <class Sys, class T, int N>
+inline void tsit5_stages(const Vec<T, N>& uprev, const T* p, T t, T dt, const Vec<T, N>& k1,
+                         Vec<T, N>& k2, Vec<T, N>& k3, Vec<T, N>& k4, Vec<T, N>& k5,
+                         Vec<T, N>& k6, Vec<T, N>& k7, Vec<T, N>& u) {
+  using C = TS<T>;
+  Vec<T, N> tmp = muladd(dt * C::a21, k1, uprev);                                   // :99
+  k2 = Sys::f(tmp, p, fmaT(C::c1, dt, t));                                          // :100
+  tmp = muladd(dt, msum(C::a31, k1, C::a32, k2), uprev);                            // :101
+  k3 = Sys::f(tmp, p, fmaT(C::c2, dt, t));
+  tmp = muladd(dt, msum(C::a41, k1, C::a42, k2, C::a43, k3), uprev);                // :103
+  k4 = Sys::f(tmp, p, fmaT(C::c3, dt, t));
+  tmp = muladd(dt, msum(C::a51, k1, C::a52, k2, C::a53, k3, C::a54, k4), uprev);    // :105
+  k5 = Sys::f(tmp, p, fmaT(C::c4, dt, t));
+  tmp = muladd(dt, msum(C::a61, k1, C::a62, k2, C::a63, k3, C::a64, k4, C::a65, k5), uprev);  // :107
+  k6 = Sys::f(tmp, p, t + dt);
+  u = muladd(dt, msum(C::a71, k1, C::a72, k2, C::a73, k3, C::a74, k4, C::a75, k5, C::a76, k6), uprev);  // :109
+  k7 = Sys::f(u, p, t + dt);                                                        // :110
+}
+
+template <class T, int N>
+inline Vec<T, N> tsit5_dense(T th, T dt, const Vec<T, N>& uprev, const Vec<T, N>& k1,
+                             const Vec<T, N>& k2, const Vec<T, N>& k3, const Vec<T, N>& k4,
+                             const Vec<T, N>& k5, const Vec<T, N>& k6, const Vec<T, N>& k7) {
+  T b[7];
+  tsit5_bthetas(th, b);                                                             // :119
+  return muladd(dt, msum(b[0], k1, b[1], k2, b[2], k3, b[3], k4, b[4], k5, b[5], k6, b[6], k7), uprev);  // :120-125
+}
+
+// ---- GPUSimpleTsit5: src/tsit5/gpuatsit5.jl:55-147
+template <class Sys, class T>
+void solve_tsit5(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  T t = J.t0;                                                                       // :67
+  int64_t cur_t = 0;  // 0-based index of the next save slot (reference: cur_t = 1)
+  int64_t slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) { O.put(slot++, u0, J.t0, J.max_out); }        // :71-75
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) {          // :79-82
+    O.put(0, u0, J.saveat[0], J.max_out);
+    cur_t = 1;
+  }
+  V u = u0;
+  V k7 = Sys::f(u, p, t);                                                           // :86
+  V k1, k2, k3, k4, k5, k6;
+  for (int64_t i = 1; i <= J.n_steps; ++i) {                                        // :95 (i = 2:length(_ts))
+    V uprev = u;
+    k1 = k7;
+    t = J.tgrid[i - 1];                                                             // :98  _ts[i-1]
+    tsit5_stages<Sys, T, N>(uprev, p, t, J.dt, k1, k2, k3, k4, k5, k6, k7, u);
+    t += J.dt;                                                                      // :111
+    if (J.save_mode == SAVE_EVERYSTEP) {
+      O.put(slot++, u, t, J.max_out);                                               // :113-114
+    } else if (J.save_mode == SAVE_SAVEAT) {
+      while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                            // :116
+        T savet = J.saveat[cur_t];
+        T th = (savet - (t - J.dt)) / J.dt;                                         // :118
+        O.put(cur_t, tsit5_dense(th, J.dt, uprev, k1, k2, k3, k4, k5, k6, k7), savet, J.max_out);
+        cur_t += 1;
+      }
+    }
+  }
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }        // :131-134
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = (int32_t)J.n_steps; O.nreject = 0; O.retcode = RET_DEFAULT;
+}
+
+// ------------------------------------------------------------------------------------
+// adaptive controller shared by ATsit5 / AVern7 / AVern9
+// (gpuatsit5.jl:279-299, gpuvern7.jl:406-426, gpuvern9.jl:575-595; constants SimpleDiffEq.jl:67-77)
+// ------------------------------------------------------------------------------------
+template <class T>
+struct Controller {
+  T beta1 = T(7.0 / 50.0), beta2 = T(2.0 / 25.0), qmax = T(10.0), qmin = T(1.0 / 5.0),
+    gamma = T(9.0 / 10.0), qoldinit = T(1.0e-4);
+  T qold = T(1.0e-4);
+};
+
+// error scaling + norm: tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol); ODE_DEFAULT_NORM
+template <class T, int N>
+inline T scaled_error_norm(const Vec<T, N>& e, const Vec<T, N>& uprev, const Vec<T, N>& u, T abstol, T reltol) {
+  Vec<T, N> s;
+  for (int i = 0; i < N; ++i) {
+    T m = jl_max(std::fabs(uprev[i]), std::fabs(u[i]));
+    s[i] = e[i] / (abstol + m * reltol);   // unfused (A3)
+  }
+  return ode_default_norm(s);
+}
+
+// returns true on accept. Updates dt, t, told, dtold, ctrl.qold.   thr = 1e-14 (or 1f-7 for AVern9)
+template <class T>
+inline bool controller_step(Controller<T>& c, T EEst, T& dt, T& t, T tf, T& told, T& dtold, double thr) {
+  T q11 = std::pow(EEst, c.beta1);                                                  // @fastmath EEst^beta1
+  T q;
+  if (EEst == T(0)) q = T(1) / c.qmax;                                              // iszero(EEst) -> inv(qmax)
+  else q = q11 / std::pow(c.qold, c.beta2);
+  if (EEst > T(1)) {
+    dt = dt / jl_min(T(1) / c.qmin, q11 / c.gamma);                                 // reject
+    return false;
+  }
+  q = max_fast(T(1) / c.qmax, min_fast(T(1) / c.qmin, q / c.gamma));
+  c.qold = jl_max(EEst, c.qoldinit);
+  dtold = dt;
+  dt = dt / q;
+  dt = jl_min(std::fabs(dt), std::fabs(tf - t - dtold));
+  told = t;
+  if ((double)(tf - t - dtold) < thr) t = tf;
+  else t += dtold;
+  return true;
+}
+
+// ---- GPUSimpleATsit5: src/tsit5/gpuatsit5.jl:205-336
+template <class Sys, class T>
+void solve_atsit5(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  using C = TS<T>;
+  Controller<T> ctrl;
+  T t = J.t0, tf = J.tf, dt = J.dt;
+  int64_t cur_t = 0, slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.t0, J.max_out);
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) { O.put(0, u0, J.saveat[0], J.max_out); cur_t = 1; }
+  V u = u0;
+  V k7 = Sys::f(u, p, t);                                                           // :240
+  V k1, k2, k3, k4, k5, k6;
+  int32_t nacc = 0, nrej = 0, ret = RET_DEFAULT;
+  int64_t attempts = 0;
+  T told = t, dtold = dt;
+  while (t < tf) {                                                                  // :250
+    V uprev = u;
+    k1 = k7;                                                                        // :252
+    bool accepted = false;
+    while (!accepted) {                                                             // :255 (EEst = Inf; while EEst > 1)
+      if ((double)dt < 1.0e-14) { ret = RET_DTMIN; goto done; }                     // :256
+      if (J.max_attempts && attempts >= J.max_attempts) { ret = RET_MAXITERS; goto done; }
+      ++attempts;
+      tsit5_stages<Sys, T, N>(uprev, p, t, dt, k1, k2, k3, k4, k5, k6, k7, u);        // :258-270
+      V e = mul(dt, msum(C::btilde1, k1, C::btilde2, k2, C::btilde3, k3, C::btilde4, k4,
+                         C::btilde5, k5, C::btilde6, k6, C::btilde7, k7));          // :272-275
+      T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :276-277
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14);      // :279-299
+      if (!accepted) { ++nrej; continue; }
+      ++nacc;
+      if (J.save_mode == SAVE_EVERYSTEP) {
+        O.put(slot++, u, t, J.max_out);                                             // :301-303
+      } else if (J.save_mode == SAVE_SAVEAT) {
+        while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                          // :305
+          T savet = J.saveat[cur_t];
+          T th = (savet - told) / dtold;                                            // :307
+          O.put(cur_t, tsit5_dense(th, dtold, uprev, k1, k2, k3, k4, k5, k6, k7), savet, J.max_out);
+          cur_t += 1;
+        }
+      }
+    }
+  }
+done:
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }        // :322-325
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = nacc; O.nreject = nrej; O.retcode = ret;
+}
+
+// ---- GPUSimpleRK4: src/rk4/gpurk4.jl:53-98  (always saves every step; SAVE_ENDPOINT keeps only the last)
+template <class Sys, class T>
+void solve_rk4(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  const T half = T(0.5);            // convert(eltype(u0), 1//2)   :69
+  const T sixth = T(1) / T(6);      // convert(eltype(u0), 1//6)   :70  (Rational -> T(num)/T(den))
+  const T two = T(2);
+  T dt = J.dt;
+  int64_t slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.tgrid ? J.tgrid[0] : J.t0, J.max_out);  // :67 us[1] = u0
+  V u = u0;
+  T t = J.t0;
+  for (int64_t i = 1; i <= J.n_steps; ++i) {                                        // :72  i in 2:length(ts)
+    V uprev = u;
+    t = J.tgrid[i];                                                                 // :74  t = ts[i]  (quirk Q1: END of step)
+    V k1 = Sys::f(u, p, t);                                                         // :75
+    V tmp = muladd(dt * half, k1, uprev);                                           // :76
+    V k2 = Sys::f(tmp, p, fmaT(half, dt, t));                                       // :77
+    tmp = muladd(dt * half, k2, uprev);                                             // :78
+    V k3 = Sys::f(tmp, p, fmaT(half, dt, t));                                       // :79
+    tmp = muladd(dt, k3, uprev);                                                    // :80
+    V k4 = Sys::f(tmp, p, t + dt);                                                  // :81
+    // :83  u = uprev + dt*sixth*(k1 + 2k2 + 2k3 + k4)
+    //      -> muladd(dt*sixth, muladd(2,k3, muladd(2,k2, k1+k4)), uprev)
+    u = muladd(dt * sixth, muladd(two, k3, muladd(two, k2, add(k1, k4))), uprev);
+    if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);              // :84 us[i] = u ; ts[i]
+  }
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = slot;
+  O.naccept = (int32_t)J.n_steps; O.nreject = 0; O.retcode = RET_DEFAULT;
+}
+
+// ------------------------------------------------------------------------------------
+// Vern7
+// ------------------------------------------------------------------------------------
+template <class T> using V7 = oracle_tab::Vern7Tab<T>;
+
+template <class T, int N>
+struct K7 { Vec<T, N> k1, k2, k3, k4, k5, k6, k7, k8, k9, k10, k11, k12, k13, k14, k15, k16; };
+
+// stages of gpuvern7.jl:107-136 (fixed) == :360-395 (adaptive)
+template <class Sys, class T, int N>
+inline void vern7_stages(const Vec<T, N>& uprev, const T* p, T t, T dt, K7<T, N>& K, Vec<T, N>& u) {
+  using C = V7<T>;
+  K.k1 = Sys::f(uprev, p, t);                                                       // :107
+  T a = dt * C::a021;                                                               // :108
+  K.k2 = Sys::f(muladd(a, K.k1, uprev), p, fmaT(C::c2, dt, t));                     // :109
+  K.k3 = Sys::f(muladd(dt, msum(C::a031, K.k1, C::a032, K.k2), uprev), p, fmaT(C::c3, dt, t));
+  K.k4 = Sys::f(muladd(dt, msum(C::a041, K.k1, C::a043, K.k3), uprev), p, fmaT(C::c4, dt, t));
+  K.k5 = Sys::f(muladd(dt, msum(C::a051, K.k1, C::a053, K.k3, C::a054, K.k4), uprev), p, fmaT(C::c5, dt, t));
+  K.k6 = Sys::f(muladd(dt, msum(C::a061, K.k1, C::a063, K.k3, C::a064, K.k4, C::a065, K.k5), uprev), p, fmaT(C::c6, dt, t));
+  K.k7 = Sys::f(muladd(dt, msum(C::a071, K.k1, C::a073, K.k3, C::a074, K.k4, C::a075, K.k5, C::a076, K.k6), uprev), p, fmaT(C::c7, dt, t));
+  K.k8 = Sys::f(muladd(dt, msum(C::a081, K.k1, C::a083, K.k3, C::a084, K.k4, C::a085, K.k5, C::a086, K.k6, C::a087, K.k7), uprev), p, fmaT(C::c8, dt, t));
+  Vec<T, N> g9 = muladd(dt, msum(C::a091, K.k1, C::a093, K.k3, C::a094, K.k4, C::a095, K.k5, C::a096, K.k6, C::a097, K.k7, C::a098, K.k8), uprev);  // :124-129
+  Vec<T, N> g10 = muladd(dt, msum(C::a101, K.k1, C::a103, K.k3, C::a104, K.k4, C::a105, K.k5, C::a106, K.k6, C::a107, K.k7), uprev);                // :130-131
+  K.k9 = Sys::f(g9, p, t + dt);                                                     // :132
+  K.k10 = Sys::f(g10, p, t + dt);                                                   // :133
+  u = muladd(dt, msum(C::b1, K.k1, C::b4, K.k4, C::b5, K.k5, C::b6, K.k6, C::b7, K.k7, C::b8, K.k8, C::b9, K.k9), uprev);  // :135-136
+}
+
+// verner_tableaus.jl:1337-1360
+template <class T>
+inline void vern7_bthetas(T th, T (&b)[13]) {
+  using C = V7<T>;
+  const T z = T(0);
+  b[0] = evalpoly<T>(th, {z, C::r011, C::r012, C::r013, C::r014, C::r015, C::r016, C::r017});
+  b[1] = evalpoly<T>(th, {z, z, C::r042, C::r043, C::r044, C::r045, C::r046, C::r047});
+  b[2] = evalpoly<T>(th, {z, z, C::r052, C::r053, C::r054, C::r055, C::r056, C::r057});
+  b[3] = evalpoly<T>(th, {z, z, C::r062, C::r063, C::r064, C::r065, C::r066, C::r067});
+  b[4] = evalpoly<T>(th, {z, z, C::r072, C::r073, C::r074, C::r075, C::r076, C::r077});
+  b[5] = evalpoly<T>(th, {z, z, C::r082, C::r083, C::r084, C::r085, C::r086, C::r087});
+  b[6] = evalpoly<T>(th, {z, z, C::r092, C::r093, C::r094, C::r095, C::r096, C::r097});
+  b[7] = evalpoly<T>(th, {z, z, C::r112, C::r113, C::r114, C::r115, C::r116, C::r117});
+  b[8] = evalpoly<T>(th, {z, z, C::r122, C::r123, C::r124, C::r125, C::r126, C::r127});
+  b[9] = evalpoly<T>(th, {z, z, C::r132, C::r133, C::r134, C::r135, C::r136, C::r137});
+  b[10] = evalpoly<T>(th, {z, z, C::r142, C::r143, C::r144, C::r145, C::r146, C::r147});
+  b[11] = evalpoly<T>(th, {z, z, C::r152, C::r153, C::r154, C::r155, C::r156, C::r157});
+  b[12] = evalpoly<T>(th, {z, z, C::r162, C::r163, C::r164, C::r165, C::r166, C::r167});
+}
+
+// extra stages + dense output of gpuvern7.jl:153-219 (fixed; dtx = dt) == :441-513 (adaptive; dtx = dtold).
+// tx is the time base the reference passes to f: the ALREADY ADVANCED t in both (quirk Q3).
+template <class Sys, class T, int N>
+inline Vec<T, N> vern7_dense(T th, const Vec<T, N>& uprev, const T* p, T tx, T dtx, K7<T, N>& K) {
+  using C = V7<T>;
+  T b[13];
+  vern7_bthetas(th, b);
+  K.k11 = Sys::f(muladd(dtx, msum(C::a1101, K.k1, C::a1104, K.k4, C::a1105, K.k5, C::a1106, K.k6, C::a1107, K.k7, C::a1108, K.k8, C::a1109, K.k9), uprev), p, fmaT(C::c11, dtx, tx));
+  K.k12 = Sys::f(muladd(dtx, msum(C::a1201, K.k1, C::a1204, K.k4, C::a1205, K.k5, C::a1206, K.k6, C::a1207, K.k7, C::a1208, K.k8, C::a1209, K.k9, C::a1211, K.k11), uprev), p, fmaT(C::c12, dtx, tx));
+  K.k13 = Sys::f(muladd(dtx, msum(C::a1301, K.k1, C::a1304, K.k4, C::a1305, K.k5, C::a1306, K.k6, C::a1307, K.k7, C::a1308, K.k8, C::a1309, K.k9, C::a1311, K.k11, C::a1312, K.k12), uprev), p, fmaT(C::c13, dtx, tx));
+  K.k14 = Sys::f(muladd(dtx, msum(C::a1401, K.k1, C::a1404, K.k4, C::a1405, K.k5, C::a1406, K.k6, C::a1407, K.k7, C::a1408, K.k8, C::a1409, K.k9, C::a1411, K.k11, C::a1412, K.k12, C::a1413, K.k13), uprev), p, fmaT(C::c14, dtx, tx));
+  K.k15 = Sys::f(muladd(dtx, msum(C::a1501, K.k1, C::a1504, K.k4, C::a1505, K.k5, C::a1506, K.k6, C::a1507, K.k7, C::a1508, K.k8, C::a1509, K.k9, C::a1511, K.k11, C::a1512, K.k12, C::a1513, K.k13), uprev), p, fmaT(C::c15, dtx, tx));
+  K.k16 = Sys::f(muladd(dtx, msum(C::a1601, K.k1, C::a1604, K.k4, C::a1605, K.k5, C::a1606, K.k6, C::a1607, K.k7, C::a1608, K.k8, C::a1609, K.k9, C::a1611, K.k11, C::a1612, K.k12, C::a1613, K.k13), uprev), p, fmaT(C::c16, dtx, tx));
+  // :212-219   uprev + dt*(k1*b1Θ + k4*b4Θ + ... + k16*b16Θ)
+  return muladd(dtx, msum(b[0], K.k1, b[1], K.k4, b[2], K.k5, b[3], K.k6, b[4], K.k7, b[5], K.k8, b[6], K.k9,
+                          b[7], K.k11, b[8], K.k12, b[9], K.k13, b[10], K.k14, b[11], K.k15, b[12], K.k16), uprev);
+}
+
+// ---- GPUSimpleVern7: src/verner/gpuvern7.jl:55-242
+template <class Sys, class T>
+void solve_vern7(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  T t = J.t0, dt = J.dt;
+  int64_t cur_t = 0, slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.t0, J.max_out);
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) { O.put(0, u0, J.saveat[0], J.max_out); cur_t = 1; }
+  V u = u0;
+  K7<T, N> K;
+  for (int64_t i = 1; i <= J.n_steps; ++i) {                                        // :104
+    V uprev = u;
+    t = J.tgrid[i - 1];                                                             // :106
+    vern7_stages<Sys, T, N>(uprev, p, t, dt, K, u);
+    t += dt;                                                                        // :138
+    if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);
+    else if (J.save_mode == SAVE_SAVEAT) {
+      while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                            // :143
+        T savet = J.saveat[cur_t];
+        T th = (savet - (t - dt)) / dt;                                             // :145
+        O.put(cur_t, vern7_dense<Sys, T, N>(th, uprev, p, t, dt, K), savet, J.max_out);
+        cur_t += 1;
+      }
+    }
+  }
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = (int32_t)J.n_steps; O.nreject = 0; O.retcode = RET_DEFAULT;
+}
+
+// ---- GPUSimpleAVern7: src/verner/gpuvern7.jl:300-536
+template <class Sys, class T>
+void solve_avern7(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  using C = V7<T>;
+  Controller<T> ctrl;
+  T t = J.t0, tf = J.tf, dt = J.dt;
+  int64_t cur_t = 0, slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.t0, J.max_out);
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) { O.put(0, u0, J.saveat[0], J.max_out); cur_t = 1; }
+  V u = u0;
+  K7<T, N> K;
+  int32_t nacc = 0, nrej = 0, ret = RET_DEFAULT;
+  int64_t attempts = 0;
+  T told = t, dtold = dt;
+  while (t < tf) {                                                                  // :353
+    V uprev = u;
+    bool accepted = false;
+    while (!accepted) {
+      if ((double)dt < 1.0e-14) { ret = RET_DTMIN; goto done; }                     // :358
+      if (J.max_attempts && attempts >= J.max_attempts) { ret = RET_MAXITERS; goto done; }
+      ++attempts;
+      vern7_stages<Sys, T, N>(uprev, p, t, dt, K, u);                               // :360-395
+      V e = mul(dt, msum(C::btilde1, K.k1, C::btilde4, K.k4, C::btilde5, K.k5, C::btilde6, K.k6,
+                         C::btilde7, K.k7, C::btilde8, K.k8, C::btilde9, K.k9, C::btilde10, K.k10));  // :397-402
+      T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :403-404
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14);      // :406-426
+      if (!accepted) { ++nrej; continue; }
+      ++nacc;
+      if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);
+      else if (J.save_mode == SAVE_SAVEAT) {
+        while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                          // :431
+          T savet = J.saveat[cur_t];
+          T th = (savet - told) / dtold;                                            // :433
+          // extra-stage times are `t + cXX*dtold` with the advanced t (Q3)      // :449
+          O.put(cur_t, vern7_dense<Sys, T, N>(th, uprev, p, t, dtold, K), savet, J.max_out);
+          cur_t += 1;
+        }
+      }
+    }
+  }
+done:
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = nacc; O.nreject = nrej; O.retcode = ret;
+}
+
+// ------------------------------------------------------------------------------------
+// Vern9.  K.k[s] holds the TRUE stage s (1..26); the reference's variable renaming
+// (gpuvern9.jl:564-573, adaptive only) is expressed by which stages the dense output reads.
+// ------------------------------------------------------------------------------------
+template <class T> using V9 = oracle_tab::Vern9Tab<T>;
+template <class T, int N> struct K9 { Vec<T, N> k[27]; };
+
+// gpuvern9.jl:105-183 (fixed, without k16) == :468-554 (adaptive)
+template <class Sys, class T, int N>
+inline void vern9_stages(const Vec<T, N>& uprev, const T* p, T t, T dt, K9<T, N>& K, Vec<T, N>& u, bool need16) {
+  using C = V9<T>;
+  auto* k = K.k;
+  k[1] = Sys::f(uprev, p, t);
+  T a = dt * C::a0201;
+  k[2] = Sys::f(muladd(a, k[1], uprev), p, fmaT(C::c1, dt, t));
+  k[3] = Sys::f(muladd(dt, msum(C::a0301, k[1], C::a0302, k[2]), uprev), p, fmaT(C::c2, dt, t));
+  k[4] = Sys::f(muladd(dt, msum(C::a0401, k[1], C::a0403, k[3]), uprev), p, fmaT(C::c3, dt, t));
+  k[5] = Sys::f(muladd(dt, msum(C::a0501, k[1], C::a0503, k[3], C::a0504, k[4]), uprev), p, fmaT(C::c4, dt, t));
+  k[6] = Sys::f(muladd(dt, msum(C::a0601, k[1], C::a0604, k[4], C::a0605, k[5]), uprev), p, fmaT(C::c5, dt, t));
+  k[7] = Sys::f(muladd(dt, msum(C::a0701, k[1], C::a0704, k[4], C::a0705, k[5], C::a0706, k[6]), uprev), p, fmaT(C::c6, dt, t));
+  k[8] = Sys::f(muladd(dt, msum(C::a0801, k[1], C::a0806, k[6], C::a0807, k[7]), uprev), p, fmaT(C::c7, dt, t));
+  k[9] = Sys::f(muladd(dt, msum(C::a0901, k[1], C::a0906, k[6], C::a0907, k[7], C::a0908, k[8]), uprev), p, fmaT(C::c8, dt, t));
+  k[10] = Sys::f(muladd(dt, msum(C::a1001, k[1], C::a1006, k[6], C::a1007, k[7], C::a1008, k[8], C::a1009, k[9]), uprev), p, fmaT(C::c9, dt, t));
+  k[11] = Sys::f(muladd(dt, msum(C::a1101, k[1], C::a1106, k[6], C::a1107, k[7], C::a1108, k[8], C::a1109, k[9], C::a1110, k[10]), uprev), p, fmaT(C::c10, dt, t));
+  k[12] = Sys::f(muladd(dt, msum(C::a1201, k[1], C::a1206, k[6], C::a1207, k[7], C::a1208, k[8], C::a1209, k[9], C::a1210, k[10], C::a1211, k[11]), uprev), p, fmaT(C::c11, dt, t));
+  k[13] = Sys::f(muladd(dt, msum(C::a1301, k[1], C::a1306, k[6], C::a1307, k[7], C::a1308, k[8], C::a1309, k[9], C::a1310, k[10], C::a1311, k[11], C::a1312, k[12]), uprev), p, fmaT(C::c12, dt, t));
+  k[14] = Sys::f(muladd(dt, msum(C::a1401, k[1], C::a1406, k[6], C::a1407, k[7], C::a1408, k[8], C::a1409, k[9], C::a1410, k[10], C::a1411, k[11], C::a1412, k[12], C::a1413, k[13]), uprev), p, fmaT(C::c13, dt, t));
+  Vec<T, N> g15 = muladd(dt, msum(C::a1501, k[1], C::a1506, k[6], C::a1507, k[7], C::a1508, k[8], C::a1509, k[9], C::a1510, k[10], C::a1511, k[11], C::a1512, k[12], C::a1513, k[13], C::a1514, k[14]), uprev);
+  k[15] = Sys::f(g15, p, t + dt);
+  if (need16) {
+    Vec<T, N> g16 = muladd(dt, msum(C::a1601, k[1], C::a1606, k[6], C::a1607, k[7], C::a1608, k[8], C::a1609, k[9], C::a1610, k[10], C::a1611, k[11], C::a1612, k[12], C::a1613, k[13]), uprev);
+    k[16] = Sys::f(g16, p, t + dt);
+  }
+  u = muladd(dt, msum(C::b1, k[1], C::b8, k[8], C::b9, k[9], C::b10, k[10], C::b11, k[11], C::b12, k[12], C::b13, k[13], C::b14, k[14], C::b15, k[15]), uprev);
+}
+
+// verner_tableaus.jl:1362-1398
+template <class T>
+inline void vern9_bthetas(T th, T (&b)[19]) {
+  using C = V9<T>;
+  const T z = T(0);
+  b[0] = evalpoly<T>(th, {z, C::r011, C::r012, C::r013, C::r014, C::r015, C::r016, C::r017, C::r018, C::r019});
+  b[1] = evalpoly<T>(th, {z, z, C::r082, C::r083, C::r084, C::r085, C::r086, C::r087, C::r088, C::r089});
+  b[2] = evalpoly<T>(th, {z, z, C::r092, C::r093, C::r094, C::r095, C::r096, C::r097, C::r098, C::r099});
+  b[3] = evalpoly<T>(th, {z, z, C::r102, C::r103, C::r104, C::r105, C::r106, C::r107, C::r108, C::r109});
+  b[4] = evalpoly<T>(th, {z, z, C::r112, C::r113, C::r114, C::r115, C::r116, C::r117, C::r118, C::r119});
+  b[5] = evalpoly<T>(th, {z, z, C::r122, C::r123, C::r124, C::r125, C::r126, C::r127, C::r128, C::r129});
+  b[6] = evalpoly<T>(th, {z, z, C::r132, C::r133, C::r134, C::r135, C::r136, C::r137, C::r138, C::r139});
+  b[7] = evalpoly<T>(th, {z, z, C::r142, C::r143, C::r144, C::r145, C::r146, C::r147, C::r148, C::r149});
+  b[8] = evalpoly<T>(th, {z, z, C::r152, C::r153, C::r154, C::r155, C::r156, C::r157, C::r158, C::r159});
+  b[9] = evalpoly<T>(th, {z, z, C::r172, C::r173, C::r174, C::r175, C::r176, C::r177, C::r178, C::r179});
+  b[10] = evalpoly<T>(th, {z, z, C::r182, C::r183, C::r184, C::r185, C::r186, C::r187, C::r188, C::r189});
+  b[11] = evalpoly<T>(th, {z, z, C::r192, C::r193, C::r194, C::r195, C::r196, C::r197, C::r198, C::r199});
+  b[12] = evalpoly<T>(th, {z, z, C::r202, C::r203, C::r204, C::r205, C::r206, C::r207, C::r208, C::r209});
+  b[13] = evalpoly<T>(th, {z, z, C::r212, C::r213, C::r214, C::r215, C::r216, C::r217, C::r218, C::r219});
+  b[14] = evalpoly<T>(th, {z, z, C::r222, C::r223, C::r224, C::r225, C::r226, C::r227, C::r228, C::r229});
+  b[15] = evalpoly<T>(th, {z, z, C::r232, C::r233, C::r234, C::r235, C::r236, C::r237, C::r238, C::r239});
+  b[16] = evalpoly<T>(th, {z, z, C::r242, C::r243, C::r244, C::r245, C::r246, C::r247, C::r248, C::r249});
+  b[17] = evalpoly<T>(th, {z, z, C::r252, C::r253, C::r254, C::r255, C::r256, C::r257, C::r258, C::r259});
+  b[18] = evalpoly<T>(th, {z, z, C::r262, C::r263, C::r264, C::r265, C::r266, C::r267, C::r268, C::r269});
+}
+
+// extra stages 17..26 + dense output.  `m` maps the reference's variable names k2..k9 at that
+// point of the code to true stages: adaptive (after the rename, :564-573): k2..k9 = stages 8..15
+// (m = 6); fixed as written (:216-331, quirk Q2): k2..k9 = stages 2..9 (m = 0).
+template <class Sys, class T, int N>
+inline Vec<T, N> vern9_dense(T th, const Vec<T, N>& uprev, const T* p, T tx, T dtx, K9<T, N>& K, int m) {
+  using C = V9<T>;
+  auto* k = K.k;
+  T b[19];
+  vern9_bthetas(th, b);
+  const Vec<T, N>&q1 = k[1], &q2 = k[2 + m], &q3 = k[3 + m], &q4 = k[4 + m], &q5 = k[5 + m], &q6 = k[6 + m],
+                 &q7 = k[7 + m], &q8 = k[8 + m], &q9 = k[9 + m];
+  k[17] = Sys::f(muladd(dtx, msum(C::a1701, q1, C::a1708, q2, C::a1709, q3, C::a1710, q4, C::a1711, q5, C::a1712, q6, C::a1713, q7, C::a1714, q8, C::a1715, q9), uprev), p, fmaT(C::c17, dtx, tx));
+  k[18] = Sys::f(muladd(dtx, msum(C::a1801, q1, C::a1808, q2, C::a1809, q3, C::a1810, q4, C::a1811, q5, C::a1812, q6, C::a1813, q7, C::a1814, q8, C::a1815, q9, C::a1817, k[17]), uprev), p, fmaT(C::c18, dtx, tx));
+  k[19] = Sys::f(muladd(dtx, msum(C::a1901, q1, C::a1908, q2, C::a1909, q3, C::a1910, q4, C::a1911, q5, C::a1912, q6, C::a1913, q7, C::a1914, q8, C::a1915, q9, C::a1917, k[17], C::a1918, k[18]), uprev), p, fmaT(C::c19, dtx, tx));
+  k[20] = Sys::f(muladd(dtx, msum(C::a2001, q1, C::a2008, q2, C::a2009, q3, C::a2010, q4, C::a2011, q5, C::a2012, q6, C::a2013, q7, C::a2014, q8, C::a2015, q9, C::a2017, k[17], C::a2018, k[18], C::a2019, k[19]), uprev), p, fmaT(C::c20, dtx, tx));
+  k[21] = Sys::f(muladd(dtx, msum(C::a2101, q1, C::a2108, q2, C::a2109, q3, C::a2110, q4, C::a2111, q5, C::a2112, q6, C::a2113, q7, C::a2114, q8, C::a2115, q9, C::a2117, k[17], C::a2118, k[18], C::a2119, k[19], C::a2120, k[20]), uprev), p, fmaT(C::c21, dtx, tx));
+  k[22] = Sys::f(muladd(dtx, msum(C::a2201, q1, C::a2208, q2, C::a2209, q3, C::a2210, q4, C::a2211, q5, C::a2212, q6, C::a2213, q7, C::a2214, q8, C::a2215, q9, C::a2217, k[17], C::a2218, k[18], C::a2219, k[19], C::a2220, k[20], C::a2221, k[21]), uprev), p, fmaT(C::c22, dtx, tx));
+  k[23] = Sys::f(muladd(dtx, msum(C::a2301, q1, C::a2308, q2, C::a2309, q3, C::a2310, q4, C::a2311, q5, C::a2312, q6, C::a2313, q7, C::a2314, q8, C::a2315, q9, C::a2317, k[17], C::a2318, k[18], C::a2319, k[19], C::a2320, k[20], C::a2321, k[21]), uprev), p, fmaT(C::c23, dtx, tx));
+  k[24] = Sys::f(muladd(dtx, msum(C::a2401, q1, C::a2408, q2, C::a2409, q3, C::a2410, q4, C::a2411, q5, C::a2412, q6, C::a2413, q7, C::a2414, q8, C::a2415, q9, C::a2417, k[17], C::a2418, k[18], C::a2419, k[19], C::a2420, k[20], C::a2421, k[21]), uprev), p, fmaT(C::c24, dtx, tx));
+  k[25] = Sys::f(muladd(dtx, msum(C::a2501, q1, C::a2508, q2, C::a2509, q3, C::a2510, q4, C::a2511, q5, C::a2512, q6, C::a2513, q7, C::a2514, q8, C::a2515, q9, C::a2517, k[17], C::a2518, k[18], C::a2519, k[19], C::a2520, k[20], C::a2521, k[21]), uprev), p, fmaT(C::c25, dtx, tx));
+  k[26] = Sys::f(muladd(dtx, msum(C::a2601, q1, C::a2608, q2, C::a2609, q3, C::a2610, q4, C::a2611, q5, C::a2612, q6, C::a2613, q7, C::a2614, q8, C::a2615, q9, C::a2617, k[17], C::a2618, k[18], C::a2619, k[19], C::a2620, k[20], C::a2621, k[21]), uprev), p, fmaT(C::c26, dtx, tx));
+  // :321-331 / :747-757
+  return muladd(dtx, msum(b[0], q1, b[1], q2, b[2], q3, b[3], q4, b[4], q5, b[5], q6, b[6], q7, b[7], q8, b[8], q9,
+                          b[9], k[17], b[10], k[18], b[11], k[19], b[12], k[20], b[13], k[21], b[14], k[22],
+                          b[15], k[23], b[16], k[24], b[17], k[25], b[18], k[26]), uprev);
+}
+
+// ---- GPUSimpleVern9: src/verner/gpuvern9.jl:55-353
+template <class Sys, class T>
+void solve_vern9(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  T t = J.t0, dt = J.dt;
+  int64_t cur_t = 0, slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.t0, J.max_out);
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) { O.put(0, u0, J.saveat[0], J.max_out); cur_t = 1; }
+  V u = u0;
+  K9<T, N> K;
+  const int m = (J.compat & COMPAT_FIX_VERN9_INTERP) ? 6 : 0;   // Q2: reference-exact pairs k2..k9
+  for (int64_t i = 1; i <= J.n_steps; ++i) {                                        // :102
+    V uprev = u;
+    t = J.tgrid[i - 1];
+    vern9_stages<Sys, T, N>(uprev, p, t, dt, K, u, false);
+    t += dt;                                                                        // :185
+    if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);
+    else if (J.save_mode == SAVE_SAVEAT) {
+      while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                            // :190
+        T savet = J.saveat[cur_t];
+        T th = (savet - (t - dt)) / dt;                                             // :192
+        O.put(cur_t, vern9_dense<Sys, T, N>(th, uprev, p, t, dt, K, m), savet, J.max_out);   // times t + c17*dt with advanced t (Q3) :222
+        cur_t += 1;
+      }
+    }
+  }
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = (int32_t)J.n_steps; O.nreject = 0; O.retcode = RET_DEFAULT;
+}
+
+// ---- GPUSimpleAVern9: src/verner/gpuvern9.jl:411-779
+template <class Sys, class T>
+void solve_avern9(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  using C = V9<T>;
+  Controller<T> ctrl;
+  const double thr = (double)1.0e-7f;   // 1.0f-7 (quirk Q4)  :466, :591
+  T t = J.t0, tf = J.tf, dt = J.dt;
+  int64_t cur_t = 0, slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.t0, J.max_out);
+  if (J.save_mode == SAVE_SAVEAT && J.n_save > 0 && J.t0 == J.saveat[0]) { O.put(0, u0, J.saveat[0], J.max_out); cur_t = 1; }
+  V u = u0;
+  K9<T, N> K;
+  auto* k = K.k;
+  int32_t nacc = 0, nrej = 0, ret = RET_DEFAULT;
+  int64_t attempts = 0;
+  T told = t, dtold = dt;
+  while (t < tf) {                                                                  // :461
+    V uprev = u;
+    bool accepted = false;
+    while (!accepted) {
+      if ((double)dt < thr) { ret = RET_DTMIN; goto done; }                         // :466
+      if (J.max_attempts && attempts >= J.max_attempts) { ret = RET_MAXITERS; goto done; }
+      ++attempts;
+      vern9_stages<Sys, T, N>(uprev, p, t, dt, K, u, true);                         // :468-554
+      V e = mul(dt, msum(C::btilde1, k[1], C::btilde8, k[8], C::btilde9, k[9], C::btilde10, k[10],
+                         C::btilde11, k[11], C::btilde12, k[12], C::btilde13, k[13], C::btilde14, k[14],
+                         C::btilde15, k[15], C::btilde16, k[16]));                  // :556-560
+      T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :561-562
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, thr);          // :575-595
+      if (!accepted) { ++nrej; continue; }
+      ++nacc;
+      if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);
+      else if (J.save_mode == SAVE_SAVEAT) {
+        while (cur_t < J.n_save && J.saveat[cur_t] <= t) {                          // :600
+          T savet = J.saveat[cur_t];
+          T th = (savet - told) / dtold;                                            // :602
+          O.put(cur_t, vern9_dense<Sys, T, N>(th, uprev, p, told, dtold, K, 6), savet, J.max_out);  // told + c17*dtold :639
+          cur_t += 1;
+        }
+      }
+    }
+  }
+done:
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = (J.save_mode == SAVE_SAVEAT) ? cur_t : slot;
+  O.naccept = nacc; O.nreject = nrej; O.retcode = ret;
+}
+
+// ------------------------------------------------------------------------------------
+// ensemble driver: the analogue of EnsembleThreads (one trajectory per task, no shared state)
+// ------------------------------------------------------------------------------------
+struct EnsembleArgs {
+  int alg, dtype;
+  int64_t n_traj;
+  const void* u0;   // SoA [N][n_traj]
+  const void* p;    // SoA [NP][n_traj]
+  double t0, tf, dt, abstol, reltol;
+  int64_t n_steps;
+  const void* tgrid;
+  const void* saveat;
+  int64_t n_save;
+  int save_mode, compat;
+  int64_t max_out, max_attempts;
+  void* out_u;        // [n_traj][max_out][N]
+  void* out_t;        // [n_traj][max_out] or null
+  int64_t* out_n;     // [n_traj] or null
+  int32_t* naccept;   // or null
+  int32_t* nreject;
+  int32_t* retcode;
+  int n_threads;
+  void* user_fn;
+  int n_param;        // runtime parameter count (== Sys::NP for built-ins)
+};
+
+template <class Sys, class T>
+void run_range(const EnsembleArgs& A, int64_t lo, int64_t hi) {
+  constexpr int N = Sys::N, NP = Sys::NP;
+  Job<T> J;
+  J.t0 = (T)A.t0; J.tf = (T)A.tf; J.dt = (T)A.dt; J.abstol = (T)A.abstol; J.reltol = (T)A.reltol;
+  J.n_steps = A.n_steps; J.tgrid = (const T*)A.tgrid; J.saveat = (const T*)A.saveat; J.n_save = A.n_save;
+  J.save_mode = A.save_mode; J.compat = A.compat; J.max_out = A.max_out; J.max_attempts = A.max_attempts;
+  const T* u0 = (const T*)A.u0;
+  const T* pp = (const T*)A.p;
+  for (int64_t i = lo; i < hi; ++i) {
+    Vec<T, N> u;
+    T p[NP > 0 ? NP : 1];
+    for (int c = 0; c < N; ++c) u[c] = u0[(int64_t)c * A.n_traj + i];
+    for (int c = 0; c < A.n_param && c < NP; ++c) p[c] = pp[(int64_t)c * A.n_traj + i];
+    Out<T, N> O;
+    O.u = (T*)A.out_u + i * A.max_out * N;
+    O.t = A.out_t ? (T*)A.out_t + i * A.max_out : nullptr;
+    O.n = 0; O.naccept = O.nreject = O.retcode = 0;
+    // unwritten slots (quirk Q5: `undef` in the reference) are reported as NaN
+    for (int64_t s = 0; s < A.max_out * N; ++s) O.u[s] = std::numeric_limits<T>::quiet_NaN();
+    switch (A.alg) {
+      case ALG_TSIT5: solve_tsit5<Sys, T>(J, u, p, O); break;
+      case ALG_ATSIT5: solve_atsit5<Sys, T>(J, u, p, O); break;
+      case ALG_RK4: solve_rk4<Sys, T>(J, u, p, O); break;
+      case ALG_VERN7: solve_vern7<Sys, T>(J, u, p, O); break;
+      case ALG_AVERN7: solve_avern7<Sys, T>(J, u, p, O); break;
+      case ALG_VERN9: solve_vern9<Sys, T>(J, u, p, O); break;
+      case ALG_AVERN9: solve_avern9<Sys, T>(J, u, p, O); break;
+    }
+    if (A.out_n) A.out_n[i] = O.n;
+    if (A.naccept) A.naccept[i] = O.naccept;
+    if (A.nreject) A.nreject[i] = O.nreject;
+    if (A.retcode) A.retcode[i] = O.retcode;
+  }
+}
+
+template <class Sys, class T>
+void run_threads(const EnsembleArgs& A, void (*setup)(void*) = nullptr) {
+  int nt = std::max(1, A.n_threads);
+  if (nt == 1) { if (setup) setup(A.user_fn); run_range<Sys, T>(A, 0, A.n_traj); return; }
+  // dynamic chunks: adaptive trajectories have unequal cost
+  std::atomic<int64_t> next(0);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(256, A.n_traj / (nt * 8) + 1));
+  std::vector<std::thread> th;
+  for (int w = 0; w < nt; ++w)
+    th.emplace_back([&]() {
+      if (setup) setup(A.user_fn);
+      for (;;) {
+        int64_t lo = next.fetch_add(chunk);
+        if (lo >= A.n_traj) break;
+        run_range<Sys, T>(A, lo, std::min(A.n_traj, lo + chunk));
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+template <class Sys>
+int run_sys(const EnsembleArgs& A, void (*setup)(void*) = nullptr) {
+  if (A.dtype == 0) run_threads<Sys, double>(A, setup);
+  else if (A.dtype == 1) run_threads<Sys, float>(A, setup);
+  else return -2;
+  return 0;
+}
+
+template <int N> void set_user(void* fn) { UserSys<N>::fn = fn; }
+
+}  // namespace
+
+extern "C" {
+
+// system ids (must match tests/ and bench.py; NOT shared with the product's registry header)
+enum { SYS_LORENZ = 0, SYS_VANDERPOL = 1, SYS_ROBERTSON = 2, SYS_NBODY = 3, SYS_LINEARDECAY = 4,
+       SYS_SCALARGROWTH = 5, SYS_NONAUTONOMOUS = 6, SYS_USER = 100 };
+
+int oracle_system_dims(int system, int* n_state, int* n_param) {
+  switch (system) {
+    case SYS_LORENZ: *n_state = 3; *n_param = 3; return 0;
+    case SYS_VANDERPOL: *n_state = 2; *n_param = 1; return 0;
+    case SYS_ROBERTSON: *n_state = 3; *n_param = 3; return 0;
+    case SYS_NBODY: *n_state = 12; *n_param = 3; return 0;
+    case SYS_LINEARDECAY: *n_state = 3; *n_param = 3; return 0;
+    case SYS_SCALARGROWTH: *n_state = 1; *n_param = 1; return 0;
+    case SYS_NONAUTONOMOUS: *n_state = 2; *n_param = 2; return 0;
+  }
+  return -1;
+}
+
+int oracle_solve(int system, int alg, int dtype, int64_t n_traj, const void* u0, const void* p,
+                 double t0, double tf, double dt, double abstol, double reltol, int64_t n_steps,
+                 const void* tgrid, const void* saveat, int64_t n_save, int save_mode, int compat,
+                 int64_t max_out, int64_t max_attempts, void* out_u, void* out_t, int64_t* out_n,
+                 int32_t* naccept, int32_t* nreject, int32_t* retcode, int n_threads,
+                 void* user_fn, int user_n_state, int user_n_param) {
+  EnsembleArgs A;
+  A.alg = alg; A.dtype = dtype; A.n_traj = n_traj; A.u0 = u0; A.p = p;
+  A.t0 = t0; A.tf = tf; A.dt = dt; A.abstol = abstol; A.reltol = reltol;
+  A.n_steps = n_steps; A.tgrid = tgrid; A.saveat = saveat; A.n_save = n_save;
+  A.save_mode = save_mode; A.compat = compat; A.max_out = max_out; A.max_attempts = max_attempts;
+  A.out_u = out_u; A.out_t = out_t; A.out_n = out_n; A.naccept = naccept; A.nreject = nreject;
+  A.retcode = retcode; A.n_threads = n_threads; A.user_fn = user_fn;
+  { int ns = 0, np = 0; if (system == SYS_USER) np = user_n_param; else if (oracle_system_dims(system, &ns, &np)) return -1; A.n_param = np; }
+  if (A.n_param > 8) return -3;
+  if (alg < 0 || alg > 6) return -4;
+  switch (system) {
+    case SYS_LORENZ: return run_sys<Lorenz>(A);
+    case SYS_VANDERPOL: return run_sys<VanDerPol>(A);
+    case SYS_ROBERTSON: return run_sys<Robertson>(A);
+    case SYS_NBODY: return run_sys<NBodyLite>(A);
+    case SYS_LINEARDECAY: return run_sys<LinearDecay>(A);
+    case SYS_SCALARGROWTH: return run_sys<ScalarGrowth>(A);
+    case SYS_NONAUTONOMOUS: return run_sys<NonAutonomous>(A);
+    case SYS_USER:
+      switch (user_n_state) {
+        case 1: return run_sys<UserSys<1>>(A, set_user<1>);
+        case 2: return run_sys<UserSys<2>>(A, set_user<2>);
+        case 3: return run_sys<UserSys<3>>(A, set_user<3>);
+        case 4: return run_sys<UserSys<4>>(A, set_user<4>);
+        case 6: return run_sys<UserSys<6>>(A, set_user<6>);
+      }
+      return -3;
+  }
+  return -1;
+}
+
+int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

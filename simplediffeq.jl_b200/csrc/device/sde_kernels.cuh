@@ -1,0 +1,293 @@
+// sde_kernels.cuh -- one-trajectory-per-thread ensemble integrator bodies for sm_100a.
+//
+// Two kernel shapes:
+//   fixed_body     GPUSimpleTsit5 / GPUSimpleRK4 / GPUSimpleVern7 / GPUSimpleVern9
+//                  (every trajectory takes the same n_steps -> plain grid, no divergence)
+//   adaptive_body  GPUSimpleATsit5 / GPUSimpleAVern7 / GPUSimpleAVern9
+//                  persistent CTAs; every LANE pulls its next trajectory from a global atomic
+//                  work queue (warp-aggregated atomicAdd) as soon as its current one reaches tf, so
+//                  trajectories with unequal step counts rebalance; the warp leaves when
+//                  __all_sync says no lane has work and the queue is drained.
+//
+// State, parameters and all stage vectors live in registers (arrays indexed by compile-time
+// constants after unrolling); the tableaus are read from __constant__ memory as direct
+// instruction operands.  Self-contained for NVRTC.
+#pragma once
+#include "sde_common.cuh"
+#include "sde_methods_gen.cuh"
+
+namespace sde {
+
+// ------------------------------------------------------------------------------------------
+// classic RK4 (src/rk4/gpurk4.jl:73-85).  Quirk Q1: the reference evaluates k1 at ts[i], the END
+// of the step being taken; kTimeIsStepEnd makes the caller pass that time.
+// ------------------------------------------------------------------------------------------
+template <class Sys, class T>
+struct RK4Method {
+  static constexpr int N = Sys::N;
+  static constexpr bool kFSAL = false;
+  static constexpr bool kHasExtra = false;
+  static constexpr bool kTimeIsStepEnd = true;
+  __device__ __forceinline__ void seed(const T*, const T*, T) {}
+  __device__ __forceinline__ void begin_step() {}
+  template <bool>
+  __device__ __forceinline__ void stages(const T* uprev, T* u, const T* p, T t, T dt) {
+    const T half = T(0.5);
+    const T sixth = T(1) / T(6);
+    const T two = T(2);
+    T k1[N], k2[N], k3[N], k4[N], tmp[N];
+    Sys::rhs(k1, uprev, p, t);
+    const T hdt = dt * half;
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = fma(hdt, k1[i], uprev[i]);
+    Sys::rhs(k2, tmp, p, fma(half, dt, t));
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = fma(hdt, k2[i], uprev[i]);
+    Sys::rhs(k3, tmp, p, fma(half, dt, t));
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = fma(dt, k3[i], uprev[i]);
+    Sys::rhs(k4, tmp, p, t + dt);
+    const T sdt = dt * sixth;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      u[i] = fma(sdt, fma(two, k3[i], fma(two, k2[i], k1[i] + k4[i])), uprev[i]);
+  }
+  template <bool> __device__ __forceinline__ void dense_prepare(const T*, const T*, T, T) {}
+  template <bool> __device__ __forceinline__ void dense(T, T, const T*, T*) const {}
+};
+
+template <class M> struct MethodTraits { static constexpr bool kTimeIsStepEnd = false; };
+template <class Sys, class T> struct MethodTraits<RK4Method<Sys, T>> { static constexpr bool kTimeIsStepEnd = true; };
+
+// ------------------------------------------------------------------------------------------
+// output helpers
+// ------------------------------------------------------------------------------------------
+template <class T, int N>
+__device__ __forceinline__ void put_series(const KArgs<T>& a, i64 traj, i64 slot, const T* v) {
+  if (a.layout == kLayoutTrajMajor) {
+    T* o = a.out_u + (traj * a.n_out + slot) * N;
+#pragma unroll
+    for (int c = 0; c < N; ++c) o[c] = v[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < N; ++c) a.out_u[(slot * N + c) * a.ld_out + traj] = v[c];
+  }
+}
+
+template <class T, int N>
+__device__ __forceinline__ void put_endpoint(const KArgs<T>& a, i64 traj, const T* v) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) a.out_u[(i64)c * a.ld_out + traj] = v[c];
+}
+
+template <class T, int N, int NP>
+__device__ __forceinline__ void load_problem(const KArgs<T>& a, i64 traj, T* u, T* p) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) u[c] = a.u0[(i64)c * a.ld_in + traj];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) p[c] = a.p[(i64)c * a.ld_in + traj];
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed-step body
+//   SAVE   kSaveEndpoint | kSaveAt | kSaveEveryStep
+//   Q2     reference-exact fixed-step Vern9 dense output (see sde_methods_gen.cuh)
+// Follows src/tsit5/gpuatsit5.jl:86-134, src/rk4/gpurk4.jl:66-85, src/verner/gpuvern7.jl:102-228,
+// src/verner/gpuvern9.jl:100-339.
+// ------------------------------------------------------------------------------------------
+template <class Sys, class T, class Method, int SAVE, bool Q2>
+__device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
+  constexpr int N = Sys::N, NP = Sys::NP;
+  constexpr bool kEnd = MethodTraits<Method>::kTimeIsStepEnd;
+  const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (traj >= a.n_traj) return;
+
+  T u[N], uprev[N], p[NP > 0 ? NP : 1];
+  load_problem<T, N, NP>(a, traj, u, p);
+
+  Method m;
+  T t = a.t0;
+  m.seed(u, p, t);
+  int cur = 0;
+  if (SAVE == kSaveEveryStep) put_series<T, N>(a, traj, 0, u);
+  if (SAVE == kSaveAt) {
+    if (a.n_save > 0 && a.t0 == a.saveat[0]) {   // us[1] = u0 only on exact equality (Q8)
+      put_series<T, N>(a, traj, 0, u);
+      cur = 1;
+    }
+  }
+  const T dt = a.dt;
+  for (i64 s = 1; s <= a.n_steps; ++s) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) uprev[c] = u[c];
+    m.begin_step();
+    t = kEnd ? a.tgrid[s] : a.tgrid[s - 1];      // range element, never an accumulated sum
+    m.template stages<false>(uprev, u, p, t, dt);
+    if (!kEnd) t = t + dt;
+    if (SAVE == kSaveEveryStep) put_series<T, N>(a, traj, s, u);
+    if (SAVE == kSaveAt) {
+      bool prepared = false;
+      while (cur < a.n_save && a.saveat[cur] <= t) {
+        const T savet = a.saveat[cur];
+        const T th = (savet - (t - dt)) / dt;
+        if (!prepared) {           // extra stages do not depend on theta: once per step
+          m.template dense_prepare<Q2>(uprev, p, t, dt);   // time base = advanced t (Q3)
+          prepared = true;
+        }
+        T o[N];
+        m.template dense<Q2>(th, dt, uprev, o);
+        put_series<T, N>(a, traj, cur, o);
+        ++cur;
+      }
+    }
+  }
+  if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
+}
+
+// ------------------------------------------------------------------------------------------
+// adaptive body (PI controller of src/SimpleDiffEq.jl:67-77; loop of src/tsit5/gpuatsit5.jl:250-320,
+// src/verner/gpuvern7.jl:353-520, src/verner/gpuvern9.jl:461-763)
+//   kV9   AVern9: dtmin / tf-snap thresholds are 1.0f-7 (quirk Q4) and extra-stage times use told
+// ------------------------------------------------------------------------------------------
+template <class Sys, class T, class Method, int SAVE, bool kV9>
+__device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
+  constexpr int N = Sys::N, NP = Sys::NP;
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const double thr = kV9 ? (double)1.0e-7f : 1.0e-14;
+  const T beta1 = T(7.0 / 50.0), beta2 = T(2.0 / 25.0), qmax = T(10.0), qmin = T(1.0 / 5.0),
+          gamma = T(9.0 / 10.0), qoldinit = T(1.0e-4);
+  const T inv_qmax = T(1) / qmax, inv_qmin = T(1) / qmin;
+  const T tf = a.tf;
+
+  Method m;
+  T u[N], uprev[N], p[NP > 0 ? NP : 1];
+  T t = a.t0, dt = a.dt, told = a.t0, dtold = a.dt, qold = qoldinit;
+  int cur = 0, nacc = 0, nrej = 0;
+  i64 traj = -1, attempts = 0;
+  bool active = false, drained = false, newstep = false;
+
+  for (;;) {
+    // ---- work queue: idle lanes fetch the next trajectory (one atomic per warp per refill)
+    const unsigned want = __ballot_sync(FULL, !active && !drained);
+    if (want) {
+      const int leader = __ffs(want) - 1;
+      u64 base = 0;
+      if ((int)lane == leader) base = atomicAdd(a.queue, (u64)__popc(want));
+      base = __shfl_sync(FULL, base, leader);
+      if (!active && !drained) {
+        traj = (i64)base + __popc(want & ((1u << lane) - 1u));
+        if (traj < a.n_traj) {
+          load_problem<T, N, NP>(a, traj, u, p);
+          t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
+          cur = 0; nacc = 0; nrej = 0; attempts = 0;
+          m.seed(u, p, t);
+          if (SAVE == kSaveAt) {
+            if (a.n_save > 0 && a.t0 == a.saveat[0]) {
+              put_series<T, N>(a, traj, 0, u);
+              cur = 1;
+            }
+          }
+          active = true;
+          newstep = true;
+          if (!(t < tf)) {   // `while t < tspan[2]` never entered
+            if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
+            if (a.out_t) a.out_t[traj] = t;
+            if (a.naccept) a.naccept[traj] = 0;
+            if (a.nreject) a.nreject[traj] = 0;
+            if (a.retcode) a.retcode[traj] = kRetDefault;
+            active = false;
+          }
+        } else {
+          drained = true;
+        }
+      }
+    }
+    if (__all_sync(FULL, !active)) {
+      if (__all_sync(FULL, drained)) break;   // warp-vote exit: nothing left anywhere
+      continue;
+    }
+
+    if (active) {
+      if (newstep) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) uprev[c] = u[c];
+        m.begin_step();
+        newstep = false;
+      }
+      int ret = -1;
+      if ((double)dt < thr) {
+        ret = kRetDtMin;                               // error("dt<dtmin")
+      } else if (a.max_attempts != 0 && attempts >= a.max_attempts) {
+        ret = kRetMaxIters;
+      } else {
+        ++attempts;
+        m.template stages<true>(uprev, u, p, t, dt);
+        T e[N];
+        m.error(dt, e);
+        // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
+        T EEst;
+        if (N == 1) {
+          EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
+        } else {
+          T ssum = T(0);
+#pragma unroll
+          for (int c = 0; c < N; ++c) {
+            const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+            ssum = (c == 0) ? sc * sc : ssum + sc * sc;
+          }
+          EEst = sde_sqrt(ssum / T(N));
+        }
+        const T q11 = sde_pow(EEst, beta1);
+        T q = (EEst == T(0)) ? inv_qmax : q11 / sde_pow(qold, beta2);
+        if (EEst > T(1)) {
+          dt = dt / jl_min(inv_qmin, q11 / gamma);
+          ++nrej;
+        } else {
+          q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
+          qold = jl_max(EEst, qoldinit);
+          dtold = dt;
+          dt = dt / q;
+          dt = jl_min(sde_abs(dt), sde_abs(tf - t - dtold));
+          told = t;
+          if ((double)(tf - t - dtold) < thr) t = tf;
+          else t = t + dtold;
+          ++nacc;
+          newstep = true;
+          if (SAVE == kSaveAt) {
+            bool prepared = false;
+            while (cur < a.n_save && a.saveat[cur] <= t) {
+              const T savet = a.saveat[cur];
+              const T th = (savet - told) / dtold;
+              if (!prepared) {
+                m.template dense_prepare<false>(uprev, p, kV9 ? told : t, dtold);
+                prepared = true;
+              }
+              T o[N];
+              m.template dense<false>(th, dtold, uprev, o);
+              put_series<T, N>(a, traj, cur, o);
+              ++cur;
+            }
+          }
+          if (!(t < tf)) ret = kRetDefault;
+        }
+      }
+      if (ret >= 0) {   // trajectory finished (or failed): publish and free the lane
+        if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
+        if (SAVE == kSaveAt && ret != kRetDefault) {
+          T nanv[N];
+#pragma unroll
+          for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
+          for (; cur < a.n_save; ++cur) put_series<T, N>(a, traj, cur, nanv);
+        }
+        if (a.out_t) a.out_t[traj] = t;
+        if (a.naccept) a.naccept[traj] = nacc;
+        if (a.nreject) a.nreject[traj] = nrej;
+        if (a.retcode) a.retcode[traj] = ret;
+        active = false;
+      }
+    }
+  }
+}
+
+}  // namespace sde

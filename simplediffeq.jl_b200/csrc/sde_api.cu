@@ -1,0 +1,589 @@
+// sde_api.cu -- C ABI of libsimplediffeq_cuda: system registry, NVRTC path, ensemble launcher,
+// multi-device sharder.  See include/simplediffeq_cuda.h for the contract of every entry point.
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/simplediffeq_cuda.h"
+#include "device/sde_common.cuh"
+#include "sde_builtin_decl.h"
+
+// ids in the public header and in the device headers must agree
+static_assert((int)sde::kTsit5 == SDE_ALG_TSIT5 && (int)sde::kATsit5 == SDE_ALG_ATSIT5 &&
+              (int)sde::kRK4 == SDE_ALG_RK4 && (int)sde::kVern7 == SDE_ALG_VERN7 &&
+              (int)sde::kAVern7 == SDE_ALG_AVERN7 && (int)sde::kVern9 == SDE_ALG_VERN9 &&
+              (int)sde::kAVern9 == SDE_ALG_AVERN9, "alg ids");
+static_assert((int)sde::kSaveEndpoint == SDE_SAVE_ENDPOINT && (int)sde::kSaveAt == SDE_SAVE_SAVEAT &&
+              (int)sde::kSaveEveryStep == SDE_SAVE_EVERYSTEP, "save ids");
+static_assert((int)sde::kLayoutTrajMajor == SDE_LAYOUT_TRAJ_MAJOR && (int)sde::kLayoutSoA == SDE_LAYOUT_SOA, "layout ids");
+static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin == SDE_RET_DTMIN &&
+              (int)sde::kRetMaxIters == SDE_RET_MAXITERS, "retcodes");
+static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP, "compat flags");
+
+extern const char* const sde_embedded_names[];
+extern const char* const sde_embedded_sources[];
+extern const int sde_embedded_count;
+
+namespace {
+
+constexpr int kBlock = 128;
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define SDE_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(SDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+bool is_adaptive(int alg) { return alg == SDE_ALG_ATSIT5 || alg == SDE_ALG_AVERN7 || alg == SDE_ALG_AVERN9; }
+size_t esize(int dtype) { return dtype == SDE_F64 ? 8 : 4; }
+
+struct Compiled {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  std::vector<char> cubin;
+};
+
+}  // namespace
+
+struct sde_system_s {
+  bool builtin = true;
+  std::string name;
+  int n_state = 0, n_param = 0;
+  sde_builtin_lookup_fn lookup = nullptr;
+  // NVRTC systems
+  std::string src;
+  std::mutex mu;
+  std::map<std::string, Compiled> cache;   // key: alg/dtype/save/q2[/device]
+};
+
+namespace {
+
+struct BuiltinEntry {
+  const char* name;
+  int n_state, n_param;
+  sde_builtin_lookup_fn fn;
+};
+const BuiltinEntry kBuiltins[] = {
+    {"lorenz", 3, 3, sde_lookup_lorenz},
+    {"vanderpol", 2, 1, sde_lookup_vanderpol},
+    {"robertson", 3, 3, sde_lookup_robertson},
+    {"nbody", 12, 3, sde_lookup_nbody},
+    {"lineardecay", 3, 3, sde_lookup_lineardecay},
+    {"scalargrowth", 1, 1, sde_lookup_scalargrowth},
+    {"nonautonomous", 2, 2, sde_lookup_nonautonomous},
+};
+sde_system_s g_builtin_handles[sizeof(kBuiltins) / sizeof(kBuiltins[0])];
+std::once_flag g_builtin_once;
+
+void init_builtins() {
+  for (size_t i = 0; i < sizeof(kBuiltins) / sizeof(kBuiltins[0]); ++i) {
+    g_builtin_handles[i].builtin = true;
+    g_builtin_handles[i].name = kBuiltins[i].name;
+    g_builtin_handles[i].n_state = kBuiltins[i].n_state;
+    g_builtin_handles[i].n_param = kBuiltins[i].n_param;
+    g_builtin_handles[i].lookup = kBuiltins[i].fn;
+  }
+}
+
+int validate(const sde_system_s* sys, const sde_options_t* o) {
+  if (!sys || !o) return fail(SDE_ERR_INVALID, "null system or options");
+  if (o->alg < 0 || o->alg > 6) return fail(SDE_ERR_INVALID, "unknown algorithm id %d", o->alg);
+  if (o->dtype != SDE_F64 && o->dtype != SDE_F32) return fail(SDE_ERR_INVALID, "unknown dtype %d", o->dtype);
+  if (o->save_mode < 0 || o->save_mode > 2) return fail(SDE_ERR_INVALID, "unknown save_mode %d", o->save_mode);
+  if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
+    return fail(SDE_ERR_INVALID, "unknown layout %d", o->layout);
+  if (o->n_traj < 0) return fail(SDE_ERR_INVALID, "n_traj < 0");
+  if (o->save_mode == SDE_SAVE_SAVEAT) {
+    if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(SDE_ERR_INVALID, "saveat array missing");
+    if (o->n_save > 0x7fffffff) return fail(SDE_ERR_INVALID, "n_save too large");
+    if (o->alg == SDE_ALG_RK4)
+      return fail(SDE_ERR_UNSUPPORTED, "GPUSimpleRK4 has no saveat (the reference ignores the keyword and saves every step)");
+  }
+  if (is_adaptive(o->alg)) {
+    if (o->save_mode == SDE_SAVE_EVERYSTEP)
+      return fail(SDE_ERR_UNSUPPORTED, "save_everystep=true (variable-length output) is not provided for adaptive algorithms yet");
+  } else {
+    if (o->n_steps < 0) return fail(SDE_ERR_INVALID, "n_steps < 0");
+  }
+  return SDE_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// NVRTC
+// --------------------------------------------------------------------------------------------
+const char* method_name(int alg) {
+  switch (alg) {
+    case SDE_ALG_TSIT5: case SDE_ALG_ATSIT5: return "sde::Tsit5Method";
+    case SDE_ALG_RK4: return "sde::RK4Method";
+    case SDE_ALG_VERN7: case SDE_ALG_AVERN7: return "sde::Vern7Method";
+    default: return "sde::Vern9Method";
+  }
+}
+
+std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool syntax_only) {
+  std::string s;
+  s += dtype == SDE_F64 ? "typedef double real;\n" : "typedef float real;\n";
+  s += "#include \"sde_kernels.cuh\"\n";
+  s += "#line 1 \"user_rhs.cu\"\n";
+  s += sys->src;
+  s += "\n#line 1 \"sde_user_glue.cu\"\n";
+  char buf[1024];
+  snprintf(buf, sizeof buf,
+           "struct SdeUserSys {\n"
+           "  static constexpr int N = %d, NP = %d;\n"
+           "  template <class T> __device__ __forceinline__ static void rhs(T* du, const T* u, const T* p, T t) {\n"
+           "    ::rhs(du, u, p, t);\n  }\n};\n",
+           sys->n_state, sys->n_param);
+  s += buf;
+  if (syntax_only) {
+    s += "extern \"C\" __global__ void sde_user_check(real* du, const real* u, const real* p, real t) {\n"
+         "  SdeUserSys::rhs<real>(du, u, p, t);\n}\n";
+    return s;
+  }
+  if (is_adaptive(alg)) {
+    snprintf(buf, sizeof buf,
+             "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
+             "  sde::adaptive_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s>(a);\n}\n",
+             kBlock, method_name(alg), save, alg == SDE_ALG_AVERN9 ? "true" : "false");
+  } else {
+    snprintf(buf, sizeof buf,
+             "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
+             "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s>(a);\n}\n",
+             kBlock, method_name(alg), save, q2 ? "true" : "false");
+  }
+  s += buf;
+  return s;
+}
+
+int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log) {
+  nvrtcProgram prog;
+  nvrtcResult r = nvrtcCreateProgram(&prog, program.c_str(), "sde_user.cu", sde_embedded_count,
+                                     sde_embedded_sources, sde_embedded_names);
+  if (r != NVRTC_SUCCESS) return fail(SDE_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo",
+                        "-default-device"};
+  r = nvrtcCompileProgram(prog, 5, opts);
+  size_t ls = 0;
+  nvrtcGetProgramLogSize(prog, &ls);
+  std::string lg(ls, '\0');
+  if (ls > 1) nvrtcGetProgramLog(prog, &lg[0]);
+  if (log) *log = lg;
+  if (r != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    return fail(SDE_ERR_NVRTC, "NVRTC compilation failed: %s\n%s", nvrtcGetErrorString(r), lg.c_str());
+  }
+  if (cubin) {
+    size_t cs = 0;
+    r = nvrtcGetCUBINSize(prog, &cs);
+    if (r != NVRTC_SUCCESS || cs == 0) {
+      nvrtcDestroyProgram(&prog);
+      return fail(SDE_ERR_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    cubin->resize(cs);
+    nvrtcGetCUBIN(prog, cubin->data());
+  }
+  nvrtcDestroyProgram(&prog);
+  return SDE_OK;
+}
+
+// returns the cache entry (compiled; module loaded only if `load`)
+int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
+  const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
+                  !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
+  int dev = -1;
+  if (load) SDE_CUDA(cudaGetDevice(&dev));
+  char key[96];
+  snprintf(key, sizeof key, "%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2);
+  std::lock_guard<std::mutex> lk(sys->mu);
+  Compiled& c = sys->cache[key];
+  if (c.cubin.empty()) {
+    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, false);
+    int rc = nvrtc_compile(prog, &c.cubin, nullptr);
+    if (rc != SDE_OK) { sys->cache.erase(key); return rc; }
+  }
+  if (!load) return SDE_OK;
+  // one module per device
+  char dkey[112];
+  snprintf(dkey, sizeof dkey, "%s@%d", key, dev);
+  Compiled& d = sys->cache[dkey];
+  if (!d.kernel) {
+    const std::vector<char>& cubin = sys->cache[key].cubin;
+    SDE_CUDA(cudaLibraryLoadData(&d.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    SDE_CUDA(cudaLibraryGetKernel(&d.kernel, d.lib, "sde_user_kernel"));
+  }
+  *fn = (const void*)d.kernel;
+  return SDE_OK;
+}
+
+int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
+  if (sys->builtin) {
+    const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
+                    !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
+    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode, q2);
+    if (!ki.fn)
+      return fail(SDE_ERR_UNSUPPORTED, "no kernel for system %s alg %d dtype %d save_mode %d",
+                  sys->name.c_str(), o->alg, o->dtype, o->save_mode);
+    *fn = ki.fn;
+    return SDE_OK;
+  }
+  return get_user_kernel(sys, o, load, fn);
+}
+
+// --------------------------------------------------------------------------------------------
+// launch on the current device
+// --------------------------------------------------------------------------------------------
+template <class T>
+int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const void* d_u0, const void* d_p,
+             int64_t ld_in, void* d_out_u, int64_t ld_out, void* d_out_t, int32_t* d_nacc,
+             int32_t* d_nrej, int32_t* d_ret, cudaStream_t st) {
+  const bool adaptive = is_adaptive(o->alg);
+  sde::KArgs<T> a;
+  memset(&a, 0, sizeof a);
+  a.u0 = (const T*)d_u0;
+  a.p = (const T*)d_p;
+  a.n_traj = o->n_traj;
+  a.ld_in = ld_in;
+  a.t0 = (T)o->t0; a.tf = (T)o->tf; a.dt = (T)o->dt; a.abstol = (T)o->abstol; a.reltol = (T)o->reltol;
+  a.n_steps = adaptive ? 0 : o->n_steps;
+  a.n_save = o->save_mode == SDE_SAVE_SAVEAT ? (int)o->n_save : 0;
+  a.compat = o->compat;
+  a.layout = o->layout;
+  a.max_attempts = o->max_attempts;
+  a.out_u = (T*)d_out_u;
+  a.ld_out = ld_out;
+  a.n_out = o->save_mode == SDE_SAVE_SAVEAT ? o->n_save
+            : o->save_mode == SDE_SAVE_EVERYSTEP ? o->n_steps + 1 : 1;
+  a.out_t = adaptive ? (T*)d_out_t : nullptr;
+  a.naccept = d_nacc; a.nreject = d_nrej; a.retcode = d_ret;
+
+  // small per-call device constants: time grid, saveat, queue head
+  const size_t ng = adaptive ? 0 : (size_t)o->n_steps + 1;
+  const size_t ns = (size_t)a.n_save;
+  const size_t bytes = (ng + ns) * sizeof(T) + 16;
+  char* scratch = nullptr;
+  SDE_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
+  SDE_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
+  a.queue = (sde::u64*)scratch;
+  T* d_grid = (T*)(scratch + 16);
+  std::vector<T> host((ng + ns));
+  if (ng) {
+    if (o->tgrid) memcpy(host.data(), o->tgrid, ng * sizeof(T));
+    else for (size_t k = 0; k < ng; ++k) host[k] = (T)o->t0 + (T)((T)k * (T)o->dt);
+    a.tgrid = d_grid;
+  }
+  if (ns) {
+    memcpy(host.data() + ng, o->saveat, ns * sizeof(T));
+    a.saveat = d_grid + ng;
+  }
+  if (ng + ns) {
+    SDE_CUDA(cudaMemcpyAsync(d_grid, host.data(), (ng + ns) * sizeof(T), cudaMemcpyHostToDevice, st));
+    // the pageable source is staged by the runtime before the call returns, so `host` may die
+  }
+
+  if (o->n_traj > 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    SDE_CUDA(cudaGetDevice(&dev));
+    unsigned grid;
+    const int64_t full = (o->n_traj + kBlock - 1) / kBlock;
+    if (adaptive) {
+      SDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+      if (per_sm < 1) per_sm = 1;
+      grid = (unsigned)std::min<int64_t>(full, (int64_t)sms * per_sm);   // persistent CTAs
+    } else {
+      if (full > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
+      grid = (unsigned)full;
+    }
+    void* params[] = {&a};
+    SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, 0, st));
+    g_launches.fetch_add(1);
+  }
+  SDE_CUDA(cudaFreeAsync(scratch, st));
+  (void)sys;
+  return SDE_OK;
+}
+
+int launch(sde_system_s* sys, const sde_options_t* o, const void* d_u0, const void* d_p, int64_t ld_in,
+           void* d_out_u, int64_t ld_out, void* d_out_t, int32_t* d_nacc, int32_t* d_nrej,
+           int32_t* d_ret, cudaStream_t st) {
+  const void* fn = nullptr;
+  int rc = get_kernel(sys, o, true, &fn);
+  if (rc != SDE_OK) return rc;
+  if (o->dtype == SDE_F64)
+    return launch_t<double>(sys, o, fn, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+  return launch_t<float>(sys, o, fn, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+}
+
+int64_t out_slots(const sde_options_t* o) {
+  return o->save_mode == SDE_SAVE_SAVEAT ? o->n_save
+         : o->save_mode == SDE_SAVE_EVERYSTEP ? o->n_steps + 1 : 1;
+}
+
+// --------------------------------------------------------------------------------------------
+// one device shard of a host-buffer solve: trajectories [lo, hi) in chunks that fit the budget
+// --------------------------------------------------------------------------------------------
+int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t lo, int64_t hi,
+                const char* u0, const char* p, char* out_u, char* out_t, int32_t* nacc, int32_t* nrej,
+                int32_t* ret, std::string* err) {
+  auto body = [&]() -> int {
+    if (device >= 0) SDE_CUDA(cudaSetDevice(device));
+    const size_t es = esize(o->dtype);
+    const int N = sys->n_state, NP = sys->n_param;
+    const int64_t n_all = o->n_traj, slots = out_slots(o);
+    const bool series = o->save_mode != SDE_SAVE_ENDPOINT;
+    const bool adaptive = is_adaptive(o->alg);
+    // device memory budget per chunk: keep well below HBM capacity
+    size_t free_b = 0, total_b = 0;
+    SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_traj = es * ((size_t)N + NP + (size_t)N * slots + 1) + 12;
+    int64_t chunk = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
+    chunk = std::min<int64_t>(chunk, hi - lo);
+    if (chunk > 32) chunk -= chunk % 32;
+    cudaStream_t st;
+    SDE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    char *d_u0 = nullptr, *d_p = nullptr, *d_out = nullptr, *d_t = nullptr;
+    int32_t *d_na = nullptr, *d_nr = nullptr, *d_rc = nullptr;
+    int rc = SDE_OK;
+    auto cleanup = [&]() {
+      cudaFree(d_u0); cudaFree(d_p); cudaFree(d_out); cudaFree(d_t); cudaFree(d_na); cudaFree(d_nr); cudaFree(d_rc);
+      cudaStreamDestroy(st);
+    };
+#define SDE_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+      return fail(SDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    if (chunk > 0) {
+      SDE_TRY(cudaMalloc((void**)&d_u0, es * N * chunk));
+      if (NP) SDE_TRY(cudaMalloc((void**)&d_p, es * NP * chunk));
+      SDE_TRY(cudaMalloc((void**)&d_out, es * N * slots * chunk));
+      if (adaptive && out_t) SDE_TRY(cudaMalloc((void**)&d_t, es * chunk));
+      if (nacc) SDE_TRY(cudaMalloc((void**)&d_na, 4 * chunk));
+      if (nrej) SDE_TRY(cudaMalloc((void**)&d_nr, 4 * chunk));
+      if (ret) SDE_TRY(cudaMalloc((void**)&d_rc, 4 * chunk));
+    }
+    for (int64_t c0 = lo; c0 < hi; c0 += chunk) {
+      const int64_t n = std::min<int64_t>(chunk, hi - c0);
+      // H2D: SoA rows of the shard (host pitch = n_all elements, device pitch = chunk elements)
+      SDE_TRY(cudaMemcpy2DAsync(d_u0, es * chunk, u0 + es * c0, es * n_all, es * n, N, cudaMemcpyHostToDevice, st));
+      if (NP) SDE_TRY(cudaMemcpy2DAsync(d_p, es * chunk, p + es * c0, es * n_all, es * n, NP, cudaMemcpyHostToDevice, st));
+      sde_options_t oc = *o;
+      oc.n_traj = n;
+      rc = launch(sys, &oc, d_u0, d_p, chunk, d_out, chunk, d_t, d_na, d_nr, d_rc, st);
+      if (rc != SDE_OK) { cleanup(); return rc; }
+      // D2H
+      if (!series) {
+        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, d_out, es * chunk, es * n, N, cudaMemcpyDeviceToHost, st));
+      } else if (o->layout == SDE_LAYOUT_TRAJ_MAJOR) {
+        SDE_TRY(cudaMemcpyAsync(out_u + es * N * slots * c0, d_out, es * N * slots * n, cudaMemcpyDeviceToHost, st));
+      } else {
+        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, d_out, es * chunk, es * n, (size_t)N * slots, cudaMemcpyDeviceToHost, st));
+      }
+      if (d_t) SDE_TRY(cudaMemcpyAsync(out_t + es * c0, d_t, es * n, cudaMemcpyDeviceToHost, st));
+      if (d_na) SDE_TRY(cudaMemcpyAsync(nacc + c0, d_na, 4 * n, cudaMemcpyDeviceToHost, st));
+      if (d_nr) SDE_TRY(cudaMemcpyAsync(nrej + c0, d_nr, 4 * n, cudaMemcpyDeviceToHost, st));
+      if (d_rc) SDE_TRY(cudaMemcpyAsync(ret + c0, d_rc, 4 * n, cudaMemcpyDeviceToHost, st));
+      SDE_TRY(cudaStreamSynchronize(st));
+    }
+#undef SDE_TRY
+    cleanup();
+    return SDE_OK;
+  };
+  int rc = body();
+  if (rc != SDE_OK && err) *err = g_err;
+  return rc;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// exported functions
+// ==============================================================================================
+extern "C" {
+
+int sde_version(void) { return SDE_VERSION; }
+
+const char* sde_last_error(void) { return g_err.c_str(); }
+
+int sde_device_count(int* count) {
+  if (!count) return fail(SDE_ERR_INVALID, "null count");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(SDE_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return SDE_OK;
+}
+
+int sde_system_builtin(const char* name, sde_system_t* out) {
+  if (!name || !out) return fail(SDE_ERR_INVALID, "null argument");
+  std::call_once(g_builtin_once, init_builtins);
+  for (size_t i = 0; i < sizeof(kBuiltins) / sizeof(kBuiltins[0]); ++i)
+    if (!strcmp(name, kBuiltins[i].name)) {
+      *out = &g_builtin_handles[i];
+      return SDE_OK;
+    }
+  return fail(SDE_ERR_INVALID, "unknown built-in system '%s'", name);
+}
+
+int sde_system_nvrtc(const char* src, int n_state, int n_param, sde_system_t* out, char* log, size_t log_len) {
+  if (!src || !out) return fail(SDE_ERR_INVALID, "null argument");
+  if (n_state < 1 || n_state > 64 || n_param < 0 || n_param > 64)
+    return fail(SDE_ERR_INVALID, "n_state must be in 1..64 and n_param in 0..64");
+  if (log && log_len) log[0] = '\0';
+  sde_system_s* s = new sde_system_s;
+  s->builtin = false;
+  s->name = "user";
+  s->n_state = n_state;
+  s->n_param = n_param;
+  s->src = src;
+  // syntax check now (both element types must compile), kernels are built lazily
+  for (int dtype = 0; dtype < 2; ++dtype) {
+    std::string lg;
+    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, true), nullptr, &lg);
+    if (rc != SDE_OK) {
+      if (log && log_len) { strncpy(log, lg.c_str(), log_len - 1); log[log_len - 1] = '\0'; }
+      delete s;
+      return rc;
+    }
+  }
+  *out = s;
+  return SDE_OK;
+}
+
+int sde_system_dims(sde_system_t sys, int* n_state, int* n_param) {
+  if (!sys) return fail(SDE_ERR_INVALID, "null system");
+  if (n_state) *n_state = sys->n_state;
+  if (n_param) *n_param = sys->n_param;
+  return SDE_OK;
+}
+
+void sde_system_free(sde_system_t sys) {
+  if (!sys || sys->builtin) return;
+  for (auto& kv : sys->cache)
+    if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  delete sys;
+}
+
+int sde_system_prepare(sde_system_t sys, const sde_options_t* opt) {
+  int rc = validate(sys, opt);
+  if (rc != SDE_OK) return rc;
+  const void* fn = nullptr;
+  return get_kernel(sys, opt, false, &fn);
+}
+
+int sde_solve_device(sde_system_t sys, const sde_options_t* opt, const void* d_u0, const void* d_p,
+                     int64_t ld_in, void* d_out_u, int64_t ld_out, void* d_out_t, int32_t* d_naccept,
+                     int32_t* d_nreject, int32_t* d_retcode, void* stream, int async) {
+  int rc = validate(sys, opt);
+  if (rc != SDE_OK) return rc;
+  if (!d_u0 || !d_out_u || (sys->n_param > 0 && !d_p)) return fail(SDE_ERR_INVALID, "null device buffer");
+  if (ld_in < opt->n_traj || ld_out < opt->n_traj) return fail(SDE_ERR_INVALID, "ld_in / ld_out smaller than n_traj");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch(sys, opt, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_naccept, d_nreject, d_retcode, st);
+  if (rc != SDE_OK) return rc;
+  if (!async) SDE_CUDA(cudaStreamSynchronize(st));
+  return SDE_OK;
+}
+
+int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const void* p, void* out_u,
+              void* out_t, int32_t* naccept, int32_t* nreject, int32_t* retcode, const int* devices,
+              int n_dev) {
+  int rc = validate(sys, opt);
+  if (rc != SDE_OK) return rc;
+  if (!u0 || !out_u || (sys->n_param > 0 && !p)) return fail(SDE_ERR_INVALID, "null host buffer");
+  if (n_dev < 0 || (n_dev > 0 && !devices)) return fail(SDE_ERR_INVALID, "bad device list");
+  if (opt->n_traj == 0) return SDE_OK;
+  if (n_dev <= 1) {
+    return solve_shard(sys, opt, n_dev == 1 ? devices[0] : -1, 0, opt->n_traj, (const char*)u0,
+                       (const char*)p, (char*)out_u, (char*)out_t, naccept, nreject, retcode, nullptr);
+  }
+  // contiguous index ranges [g*N/G, (g+1)*N/G), one host thread + stream per device, no collective
+  std::vector<std::thread> th;
+  std::vector<int> rcs(n_dev, SDE_OK);
+  std::vector<std::string> errs(n_dev);
+  for (int g = 0; g < n_dev; ++g) {
+    const int64_t lo = opt->n_traj * g / n_dev, hi = opt->n_traj * (g + 1) / n_dev;
+    th.emplace_back([=, &rcs, &errs]() {
+      rcs[g] = solve_shard(sys, opt, devices[g], lo, hi, (const char*)u0, (const char*)p, (char*)out_u,
+                           (char*)out_t, naccept, nreject, retcode, &errs[g]);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < n_dev; ++g)
+    if (rcs[g] != SDE_OK) return fail(rcs[g], "device %d: %s", devices[g], errs[g].c_str());
+  return SDE_OK;
+}
+
+int sde_fixed_times(const sde_options_t* o, void* out, int64_t n, int64_t* n_written) {
+  if (!o || !out || !n_written) return fail(SDE_ERR_INVALID, "null argument");
+  if (is_adaptive(o->alg)) return fail(SDE_ERR_INVALID, "sde_fixed_times is for fixed-step algorithms");
+  const int64_t need = o->save_mode == SDE_SAVE_SAVEAT ? o->n_save
+                       : o->save_mode == SDE_SAVE_EVERYSTEP ? o->n_steps + 1 : 2;
+  if (n < need) return fail(SDE_ERR_INVALID, "output too small: need %lld", (long long)need);
+  auto run = [&](auto zero) {
+    using T = decltype(zero);
+    T* t = (T*)out;
+    const T* g = (const T*)o->tgrid;
+    auto grid = [&](int64_t k) -> T { return g ? g[k] : (T)((T)o->t0 + (T)((T)k * (T)o->dt)); };
+    const T dt = (T)o->dt;
+    if (o->save_mode == SDE_SAVE_SAVEAT) {
+      memcpy(t, o->saveat, sizeof(T) * o->n_save);
+    } else if (o->alg == SDE_ALG_RK4) {
+      // ts = tspan[1]:dt:tspan[2] itself (src/rk4/gpurk4.jl:65)
+      if (o->save_mode == SDE_SAVE_EVERYSTEP) for (int64_t k = 0; k <= o->n_steps; ++k) t[k] = grid(k);
+      else { t[0] = (T)o->t0; t[1] = grid(o->n_steps); }
+    } else {
+      // t = _ts[i-1]; ...; t += dt; push!(ts, t)   (src/tsit5/gpuatsit5.jl:98,111,114)
+      if (o->save_mode == SDE_SAVE_EVERYSTEP) {
+        t[0] = (T)o->t0;
+        for (int64_t k = 1; k <= o->n_steps; ++k) t[k] = (T)(grid(k - 1) + dt);
+      } else {
+        t[0] = (T)o->t0;
+        t[1] = o->n_steps > 0 ? (T)(grid(o->n_steps - 1) + dt) : (T)o->t0;
+      }
+    }
+  };
+  if (o->dtype == SDE_F64) run(0.0); else run(0.0f);
+  *n_written = need;
+  return SDE_OK;
+}
+
+int sde_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(SDE_ERR_INVALID, "null ptr");
+  SDE_CUDA(cudaMallocHost(ptr, bytes));
+  return SDE_OK;
+}
+
+int sde_host_free(void* ptr) {
+  SDE_CUDA(cudaFreeHost(ptr));
+  return SDE_OK;
+}
+
+int64_t sde_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

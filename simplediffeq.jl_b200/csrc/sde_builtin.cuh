@@ -1,0 +1,81 @@
+// sde_builtin.cuh -- __global__ wrappers + (alg, dtype, save) -> kernel table for one built-in system.
+// Each sde_sys_<name>.cu instantiates the table for its system so the systems compile in parallel.
+#pragma once
+#include "device/sde_kernels.cuh"
+#include "device/sde_systems.cuh"
+#include "sde_builtin_decl.h"
+
+#ifndef SDE_BLOCK
+#define SDE_BLOCK 128
+#endif
+
+namespace sde {
+
+template <class Sys, class T, class Method, int SAVE, bool Q2>
+__global__ void __launch_bounds__(SDE_BLOCK) fixed_kernel(const __grid_constant__ KArgs<T> a) {
+  fixed_body<Sys, T, Method, SAVE, Q2>(a);
+}
+
+template <class Sys, class T, class Method, int SAVE, bool kV9>
+__global__ void __launch_bounds__(SDE_BLOCK) adaptive_kernel(const __grid_constant__ KArgs<T> a) {
+  adaptive_body<Sys, T, Method, SAVE, kV9>(a);
+}
+
+template <class Sys, class T>
+inline KernelInfo lookup_kernel_t(int alg, int save, bool q2) {
+  using TS = Tsit5Method<Sys, T>;
+  using RK = RK4Method<Sys, T>;
+  using V7 = Vern7Method<Sys, T>;
+  using V9 = Vern9Method<Sys, T>;
+#define SDE_FIXED(M, S, Q) KernelInfo{(const void*)&fixed_kernel<Sys, T, M, S, Q>, false}
+#define SDE_ADAPT(M, S, V) KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V>, true}
+  switch (alg) {
+    case kTsit5:
+      if (save == kSaveEndpoint) return SDE_FIXED(TS, kSaveEndpoint, false);
+      if (save == kSaveAt) return SDE_FIXED(TS, kSaveAt, false);
+      if (save == kSaveEveryStep) return SDE_FIXED(TS, kSaveEveryStep, false);
+      break;
+    case kRK4:   // the reference's GPUSimpleRK4 has no saveat
+      if (save == kSaveEndpoint) return SDE_FIXED(RK, kSaveEndpoint, false);
+      if (save == kSaveEveryStep) return SDE_FIXED(RK, kSaveEveryStep, false);
+      break;
+    case kVern7:
+      if (save == kSaveEndpoint) return SDE_FIXED(V7, kSaveEndpoint, false);
+      if (save == kSaveAt) return SDE_FIXED(V7, kSaveAt, false);
+      if (save == kSaveEveryStep) return SDE_FIXED(V7, kSaveEveryStep, false);
+      break;
+    case kVern9:
+      if (save == kSaveEndpoint) return SDE_FIXED(V9, kSaveEndpoint, false);
+      if (save == kSaveAt) return q2 ? SDE_FIXED(V9, kSaveAt, true) : SDE_FIXED(V9, kSaveAt, false);
+      if (save == kSaveEveryStep) return SDE_FIXED(V9, kSaveEveryStep, false);
+      break;
+    case kATsit5:
+      if (save == kSaveEndpoint) return SDE_ADAPT(TS, kSaveEndpoint, false);
+      if (save == kSaveAt) return SDE_ADAPT(TS, kSaveAt, false);
+      break;
+    case kAVern7:
+      if (save == kSaveEndpoint) return SDE_ADAPT(V7, kSaveEndpoint, false);
+      if (save == kSaveAt) return SDE_ADAPT(V7, kSaveAt, false);
+      break;
+    case kAVern9:
+      if (save == kSaveEndpoint) return SDE_ADAPT(V9, kSaveEndpoint, true);
+      if (save == kSaveAt) return SDE_ADAPT(V9, kSaveAt, true);
+      break;
+  }
+#undef SDE_FIXED
+#undef SDE_ADAPT
+  return KernelInfo{nullptr, false};
+}
+
+template <class Sys>
+inline KernelInfo lookup_kernel(int alg, int dtype, int save, bool q2) {
+  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2)
+                    : lookup_kernel_t<Sys, float>(alg, save, q2);
+}
+
+}  // namespace sde
+
+#define SDE_DEFINE_BUILTIN(name, SysT)                                                        \
+  sde::KernelInfo sde_lookup_##name(int alg, int dtype, int save, int q2) {                   \
+    return sde::lookup_kernel<SysT>(alg, dtype, save, q2 != 0);                               \
+  }
