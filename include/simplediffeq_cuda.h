@@ -89,8 +89,13 @@ enum {
 
 /* compat flags: 0 = reproduce the reference exactly, including its quirks */
 enum {
-  SDE_COMPAT_FIX_VERN9_INTERP = 1 /* fixed-step GPUSimpleVern9 + saveat: use stages 8..15 in the dense
-                                     output (the reference uses k2..k9, src/verner/gpuvern9.jl:216-331) */
+  SDE_COMPAT_FIX_VERN9_INTERP = 1, /* fixed-step GPUSimpleVern9 + saveat: use stages 8..15 in the dense
+                                      output (the reference uses k2..k9, src/verner/gpuvern9.jl:216-331) */
+  SDE_COMPAT_STRICT_CONTROLLER = 2 /* adaptive: evaluate the PI controller literally (two pow calls, IEEE
+                                      divisions and sqrt, src/tsit5/gpuatsit5.jl:276-292) instead of the
+                                      default log2-domain evaluation of the same formulas (1 log2 + 1 exp2,
+                                      ~1e-15 relative difference in the next dt; accept/reject unchanged
+                                      except within ~1e-15 of EEst = 1) */
 };
 
 typedef struct sde_system_s* sde_system_t;
@@ -175,6 +180,10 @@ SDE_API int sde_fixed_times(const sde_options_t* opt, void* out, int64_t n, int6
 /* Pinned host memory helpers (so that the H2D/D2H copies of sde_solve run at full PCIe rate). */
 SDE_API int sde_host_alloc(void** ptr, size_t bytes);
 SDE_API int sde_host_free(void* ptr);
+
+/* Measured FMA-pipe peak of the current device (dense unrolled DFMA/FFMA chains, best of 3 after
+ * warm-up), in TFLOP/s; *ms = duration of the best run.  The roofline denominator bench.py reports. */
+SDE_API int sde_probe_fma_peak(int dtype, double* tflops, double* ms);
 
 /* Number of kernels launched by this process through the library (all threads). */
 SDE_API int64_t sde_launch_count(void);

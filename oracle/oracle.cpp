@@ -213,7 +213,10 @@ template <int NN> thread_local void* UserSys<NN>::fn = nullptr;
 enum { SAVE_ENDPOINT = 0, SAVE_SAVEAT = 1, SAVE_EVERYSTEP = 2 };
 enum { ALG_TSIT5 = 0, ALG_ATSIT5 = 1, ALG_RK4 = 2, ALG_VERN7 = 3, ALG_AVERN7 = 4, ALG_VERN9 = 5, ALG_AVERN9 = 6 };
 enum { RET_DEFAULT = 0, RET_DTMIN = 1, RET_MAXITERS = 2 };
-enum { COMPAT_FIX_VERN9_INTERP = 1 };
+enum { COMPAT_FIX_VERN9_INTERP = 1,
+       // test-only: return the neighbouring floating-point number from the controller's first pow call, to
+       // measure how sensitive step sequences are to a 1-ulp difference between libm implementations
+       COMPAT_POW_PLUS_1ULP = 16 };
 
 template <class T>
 struct Job {
@@ -351,8 +354,10 @@ inline T scaled_error_norm(const Vec<T, N>& e, const Vec<T, N>& uprev, const Vec
 
 // returns true on accept. Updates dt, t, told, dtold, ctrl.qold.   thr = 1e-14 (or 1f-7 for AVern9)
 template <class T>
-inline bool controller_step(Controller<T>& c, T EEst, T& dt, T& t, T tf, T& told, T& dtold, double thr) {
+inline bool controller_step(Controller<T>& c, T EEst, T& dt, T& t, T tf, T& told, T& dtold, double thr,
+                            bool pow_plus_1ulp = false) {
   T q11 = std::pow(EEst, c.beta1);                                                  // @fastmath EEst^beta1
+  if (pow_plus_1ulp) q11 = std::nextafter(q11, std::numeric_limits<T>::infinity());
   T q;
   if (EEst == T(0)) q = T(1) / c.qmax;                                              // iszero(EEst) -> inv(qmax)
   else q = q11 / std::pow(c.qold, c.beta2);
@@ -400,7 +405,7 @@ void solve_atsit5(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>
       V e = mul(dt, msum(C::btilde1, k1, C::btilde2, k2, C::btilde3, k3, C::btilde4, k4,
                          C::btilde5, k5, C::btilde6, k6, C::btilde7, k7));          // :272-275
       T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :276-277
-      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14);      // :279-299
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14, J.compat & COMPAT_POW_PLUS_1ULP);  // :279-299
       if (!accepted) { ++nrej; continue; }
       ++nacc;
       if (J.save_mode == SAVE_EVERYSTEP) {
@@ -578,7 +583,7 @@ void solve_avern7(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>
       V e = mul(dt, msum(C::btilde1, K.k1, C::btilde4, K.k4, C::btilde5, K.k5, C::btilde6, K.k6,
                          C::btilde7, K.k7, C::btilde8, K.k8, C::btilde9, K.k9, C::btilde10, K.k10));  // :397-402
       T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :403-404
-      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14);      // :406-426
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, 1.0e-14, J.compat & COMPAT_POW_PLUS_1ULP);  // :406-426
       if (!accepted) { ++nrej; continue; }
       ++nacc;
       if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);
@@ -750,7 +755,7 @@ void solve_avern9(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>
                          C::btilde11, k[11], C::btilde12, k[12], C::btilde13, k[13], C::btilde14, k[14],
                          C::btilde15, k[15], C::btilde16, k[16]));                  // :556-560
       T EEst = scaled_error_norm(e, uprev, u, J.abstol, J.reltol);                  // :561-562
-      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, thr);          // :575-595
+      accepted = controller_step(ctrl, EEst, dt, t, tf, told, dtold, thr, J.compat & COMPAT_POW_PLUS_1ULP);  // :575-595
       if (!accepted) { ++nrej; continue; }
       ++nacc;
       if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);

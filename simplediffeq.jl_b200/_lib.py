@@ -18,11 +18,12 @@ SAVE_ENDPOINT, SAVE_SAVEAT, SAVE_EVERYSTEP = 0, 1, 2
 LAYOUT_TRAJ_MAJOR, LAYOUT_SOA = 0, 1
 RET_DEFAULT, RET_DTMIN, RET_MAXITERS = 0, 1, 2
 COMPAT_FIX_VERN9_INTERP = 1
+COMPAT_STRICT_CONTROLLER = 2
 
 EXPORTS = ["sde_version", "sde_last_error", "sde_device_count", "sde_system_builtin",
            "sde_system_nvrtc", "sde_system_dims", "sde_system_free", "sde_system_prepare",
            "sde_solve", "sde_solve_device", "sde_fixed_times", "sde_host_alloc", "sde_host_free",
-           "sde_launch_count"]
+           "sde_launch_count", "sde_probe_fma_peak"]
 
 
 class SdeOptions(ctypes.Structure):
@@ -73,6 +74,7 @@ def lib():
     L.sde_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.sde_host_free.argtypes = [vp]
     L.sde_launch_count.restype = ctypes.c_int64
+    L.sde_probe_fma_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     for name in EXPORTS:
         if name not in ("sde_last_error", "sde_system_free", "sde_launch_count", "sde_version"):
             getattr(L, name).restype = ctypes.c_int
@@ -93,3 +95,10 @@ def device_count():
 
 def launch_count():
     return int(lib().sde_launch_count())
+
+
+def probe_fma_peak(dtype_id=SDE_F64):
+    """(TFLOP/s, ms) of the dense FMA microbenchmark on the current device."""
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    check(lib().sde_probe_fma_peak(dtype_id, ctypes.byref(tf), ctypes.byref(ms)))
+    return tf.value, ms.value

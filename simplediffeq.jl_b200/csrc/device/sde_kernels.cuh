@@ -142,14 +142,24 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     }
   }
   if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
+  if (SAVE == kSaveAt) {
+    // save points the integration never reached stay `undef` in the reference (quirk Q5): NaN here
+    if (cur < a.n_save) {
+      T nanv[N];
+#pragma unroll
+      for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
+      for (; cur < a.n_save; ++cur) put_series<T, N>(a, traj, cur, nanv);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // adaptive body (PI controller of src/SimpleDiffEq.jl:67-77; loop of src/tsit5/gpuatsit5.jl:250-320,
 // src/verner/gpuvern7.jl:353-520, src/verner/gpuvern9.jl:461-763)
 //   kV9   AVern9: dtmin / tf-snap thresholds are 1.0f-7 (quirk Q4) and extra-stage times use told
+//   kStrict  literal controller arithmetic (pow, divisions, sqrt) instead of the log2-domain one
 // ------------------------------------------------------------------------------------------
-template <class Sys, class T, class Method, int SAVE, bool kV9>
+template <class Sys, class T, class Method, int SAVE, bool kV9, bool kStrict>
 __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP;
   constexpr unsigned FULL = 0xffffffffu;
@@ -163,6 +173,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   Method m;
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
   T t = a.t0, dt = a.dt, told = a.t0, dtold = a.dt, qold = qoldinit;
+  double lqold = CtrlLog2<T>::beta2 * CtrlLog2<T>::qoldinit;   // beta2 * log2(qold)
   int cur = 0, nacc = 0, nrej = 0;
   i64 traj = -1, attempts = 0;
   bool active = false, drained = false, newstep = false;
@@ -180,6 +191,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         if (traj < a.n_traj) {
           load_problem<T, N, NP>(a, traj, u, p);
           t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
+          lqold = CtrlLog2<T>::beta2 * CtrlLog2<T>::qoldinit;
           cur = 0; nacc = 0; nrej = 0; attempts = 0;
           m.seed(u, p, t);
           if (SAVE == kSaveAt) {
@@ -225,29 +237,83 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         m.template stages<true>(uprev, u, p, t, dt);
         T e[N];
         m.error(dt, e);
-        // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
-        T EEst;
-        if (N == 1) {
-          EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
-        } else {
-          T ssum = T(0);
+        bool accept;
+        if (kStrict) {
+          // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
+          T EEst;
+          if (N == 1) {
+            EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
+          } else {
+            T ssum = T(0);
 #pragma unroll
-          for (int c = 0; c < N; ++c) {
-            const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
-            ssum = (c == 0) ? sc * sc : ssum + sc * sc;
+            for (int c = 0; c < N; ++c) {
+              const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+              ssum = (c == 0) ? sc * sc : ssum + sc * sc;
+            }
+            EEst = sde_sqrt(ssum / T(N));
           }
-          EEst = sde_sqrt(ssum / T(N));
+          const T q11 = sde_pow(EEst, beta1);
+          T q = (EEst == T(0)) ? inv_qmax : q11 / sde_pow(qold, beta2);
+          accept = !(EEst > T(1));
+          if (!accept) {
+            dt = dt / jl_min(inv_qmin, q11 / gamma);
+          } else {
+            q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
+            qold = jl_max(EEst, qoldinit);
+            dtold = dt;
+            dt = dt / q;
+          }
+        } else {
+          // same formulas in the log2 domain (see sde_common.cuh); lqold = beta2 * log2(qold)
+          using L = CtrlLog2<T>;
+          double lE;        // log2(EEst)
+          bool zero;        // iszero(EEst)
+          if (sizeof(T) == 8) {
+            // EEst^2 = sum((e_i / sc_i)^2) / N with Newton reciprocals: no division, no sqrt
+            double ss = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+              const double sc = (double)(a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+              const double x = (double)e[c] * sde_rcp_fast(sc);
+              ss = (c == 0) ? x * x : ss + x * x;
+            }
+            ss = ss * (1.0 / (double)N);
+            accept = !(ss > 1.0);
+            zero = (ss == 0.0);
+            lE = (ss != ss) ? ss : 0.5 * sde_log2_fast(ss);
+          } else {
+            // FP32 state: EEst exactly as the reference (IEEE float div / sqrt), controller in FP64
+            T EEst;
+            if (N == 1) {
+              EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
+            } else {
+              T ssum = T(0);
+#pragma unroll
+              for (int c = 0; c < N; ++c) {
+                const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+                ssum = (c == 0) ? sc * sc : ssum + sc * sc;
+              }
+              EEst = sde_sqrt(ssum / T(N));
+            }
+            accept = !(EEst > T(1));
+            zero = (EEst == T(0));
+            lE = (EEst != EEst) ? (double)EEst : sde_log2_fast((double)EEst);
+          }
+          const double l11 = L::beta1 * lE;                       // log2(EEst^beta1)
+          if (!accept) {
+            const double ld = jl_min(L::inv_qmin, l11 - L::gamma);   // min(inv(qmin), q11/gamma)
+            dt = (T)((double)dt * sde_exp2_fast(-ld));
+          } else {
+            double lq = zero ? L::inv_qmax : l11 - lqold;         // q11 / qold^beta2
+            lq = max_fast(L::inv_qmax, min_fast(L::inv_qmin, lq - L::gamma));
+            lqold = L::beta2 * jl_max(lE, L::qoldinit);           // qold = max(EEst, qoldinit)
+            dtold = dt;
+            dt = (T)((double)dt * sde_exp2_fast(-lq));
+          }
         }
-        const T q11 = sde_pow(EEst, beta1);
-        T q = (EEst == T(0)) ? inv_qmax : q11 / sde_pow(qold, beta2);
-        if (EEst > T(1)) {
-          dt = dt / jl_min(inv_qmin, q11 / gamma);
+        if (!accept) {
           ++nrej;
         } else {
-          q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
-          qold = jl_max(EEst, qoldinit);
-          dtold = dt;
-          dt = dt / q;
           dt = jl_min(sde_abs(dt), sde_abs(tf - t - dtold));
           told = t;
           if ((double)(tf - t - dtold) < thr) t = tf;
@@ -274,7 +340,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
       }
       if (ret >= 0) {   // trajectory finished (or failed): publish and free the lane
         if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
-        if (SAVE == kSaveAt && ret != kRetDefault) {
+        if (SAVE == kSaveAt && cur < a.n_save) {   // never reached (failure, or saveat beyond tf)
           T nanv[N];
 #pragma unroll
           for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));

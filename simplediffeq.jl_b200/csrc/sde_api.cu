@@ -29,7 +29,8 @@ static_assert((int)sde::kSaveEndpoint == SDE_SAVE_ENDPOINT && (int)sde::kSaveAt 
 static_assert((int)sde::kLayoutTrajMajor == SDE_LAYOUT_TRAJ_MAJOR && (int)sde::kLayoutSoA == SDE_LAYOUT_SOA, "layout ids");
 static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin == SDE_RET_DTMIN &&
               (int)sde::kRetMaxIters == SDE_RET_MAXITERS, "retcodes");
-static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP, "compat flags");
+static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP &&
+              (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER, "compat flags");
 
 extern const char* const sde_embedded_names[];
 extern const char* const sde_embedded_sources[];
@@ -145,7 +146,7 @@ const char* method_name(int alg) {
   }
 }
 
-std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool syntax_only) {
+std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool strict, bool syntax_only) {
   std::string s;
   s += dtype == SDE_F64 ? "typedef double real;\n" : "typedef float real;\n";
   s += "#include \"sde_kernels.cuh\"\n";
@@ -168,8 +169,8 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
   if (is_adaptive(alg)) {
     snprintf(buf, sizeof buf,
              "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
-             "  sde::adaptive_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s>(a);\n}\n",
-             kBlock, method_name(alg), save, alg == SDE_ALG_AVERN9 ? "true" : "false");
+             "  sde::adaptive_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
+             kBlock, method_name(alg), save, alg == SDE_ALG_AVERN9 ? "true" : "false", strict ? "true" : "false");
   } else {
     snprintf(buf, sizeof buf,
              "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
@@ -215,14 +216,15 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
 int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
   const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
                   !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
+  const bool strict = is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER);
   int dev = -1;
   if (load) SDE_CUDA(cudaGetDevice(&dev));
   char key[96];
-  snprintf(key, sizeof key, "%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2);
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict);
   std::lock_guard<std::mutex> lk(sys->mu);
   Compiled& c = sys->cache[key];
   if (c.cubin.empty()) {
-    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, false);
+    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, false);
     int rc = nvrtc_compile(prog, &c.cubin, nullptr);
     if (rc != SDE_OK) { sys->cache.erase(key); return rc; }
   }
@@ -244,7 +246,8 @@ int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void*
   if (sys->builtin) {
     const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
                     !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
-    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode, q2);
+    const bool strict = is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER);
+    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode, (q2 ? 1 : 0) | (strict ? 2 : 0));
     if (!ki.fn)
       return fail(SDE_ERR_UNSUPPORTED, "no kernel for system %s alg %d dtype %d save_mode %d",
                   sys->name.c_str(), o->alg, o->dtype, o->save_mode);
@@ -464,7 +467,7 @@ int sde_system_nvrtc(const char* src, int n_state, int n_param, sde_system_t* ou
   // syntax check now (both element types must compile), kernels are built lazily
   for (int dtype = 0; dtype < 2; ++dtype) {
     std::string lg;
-    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, true), nullptr, &lg);
+    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, false, true), nullptr, &lg);
     if (rc != SDE_OK) {
       if (log && log_len) { strncpy(log, lg.c_str(), log_len - 1); log[log_len - 1] = '\0'; }
       delete s;

@@ -16,19 +16,21 @@ __global__ void __launch_bounds__(SDE_BLOCK) fixed_kernel(const __grid_constant_
   fixed_body<Sys, T, Method, SAVE, Q2>(a);
 }
 
-template <class Sys, class T, class Method, int SAVE, bool kV9>
+template <class Sys, class T, class Method, int SAVE, bool kV9, bool kStrict>
 __global__ void __launch_bounds__(SDE_BLOCK) adaptive_kernel(const __grid_constant__ KArgs<T> a) {
-  adaptive_body<Sys, T, Method, SAVE, kV9>(a);
+  adaptive_body<Sys, T, Method, SAVE, kV9, kStrict>(a);
 }
 
 template <class Sys, class T>
-inline KernelInfo lookup_kernel_t(int alg, int save, bool q2) {
+inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict) {
   using TS = Tsit5Method<Sys, T>;
   using RK = RK4Method<Sys, T>;
   using V7 = Vern7Method<Sys, T>;
   using V9 = Vern9Method<Sys, T>;
 #define SDE_FIXED(M, S, Q) KernelInfo{(const void*)&fixed_kernel<Sys, T, M, S, Q>, false}
-#define SDE_ADAPT(M, S, V) KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V>, true}
+#define SDE_ADAPT(M, S, V)                                                       \
+  (strict ? KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, true>, true} \
+          : KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, false>, true})
   switch (alg) {
     case kTsit5:
       if (save == kSaveEndpoint) return SDE_FIXED(TS, kSaveEndpoint, false);
@@ -68,14 +70,15 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2) {
 }
 
 template <class Sys>
-inline KernelInfo lookup_kernel(int alg, int dtype, int save, bool q2) {
-  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2)
-                    : lookup_kernel_t<Sys, float>(alg, save, q2);
+inline KernelInfo lookup_kernel(int alg, int dtype, int save, int variant) {
+  const bool q2 = (variant & 1) != 0, strict = (variant & 2) != 0;
+  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2, strict)
+                    : lookup_kernel_t<Sys, float>(alg, save, q2, strict);
 }
 
 }  // namespace sde
 
 #define SDE_DEFINE_BUILTIN(name, SysT)                                                        \
-  sde::KernelInfo sde_lookup_##name(int alg, int dtype, int save, int q2) {                   \
-    return sde::lookup_kernel<SysT>(alg, dtype, save, q2 != 0);                               \
+  sde::KernelInfo sde_lookup_##name(int alg, int dtype, int save, int variant) {              \
+    return sde::lookup_kernel<SysT>(alg, dtype, save, variant);                               \
   }

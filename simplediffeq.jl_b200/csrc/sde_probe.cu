@@ -1,0 +1,65 @@
+// sde_probe.cu -- measures the roofline denominators the benchmark reports against:
+// the FP64 (and FP32) FMA-pipe peak of the device actually in use, under its real clocks/power cap.
+// MEASURED_PEAKS.json (driver-written) only has HBM and bf16-tensor figures; SURVEY.md 8d asks the
+// benchmark to measure the non-tensor FMA peak itself.
+#include <cuda_runtime.h>
+
+#include "../../include/simplediffeq_cuda.h"
+
+namespace {
+
+template <class T, int CHAINS>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) x[c] = (T)(threadIdx.x + c);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+#pragma unroll
+      for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+  }
+  T s = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) s += x[c];
+  if (s == (T)-1.2345) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <class T>
+int probe(double* tflops, double* ms_out) {
+  constexpr int CHAINS = 8;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SDE_ERR_CUDA;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  T* d = nullptr;
+  if (cudaMalloc((void**)&d, 64) != cudaSuccess) return SDE_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double best = 0, best_ms = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    fma_peak_kernel<T, CHAINS><<<blocks, threads>>>(d, iters, (T)0.999999, (T)1e-6);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return SDE_ERR_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * CHAINS * 16.0 * iters * (double)blocks * threads;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) { best = tf; best_ms = ms; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  if (ms_out) *ms_out = best_ms;
+  return SDE_OK;
+}
+
+}  // namespace
+
+extern "C" int sde_probe_fma_peak(int dtype, double* tflops, double* ms) {
+  if (!tflops) return SDE_ERR_INVALID;
+  return dtype == SDE_F64 ? probe<double>(tflops, ms) : probe<float>(tflops, ms);
+}
