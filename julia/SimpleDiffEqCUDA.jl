@@ -1,0 +1,172 @@
+# SimpleDiffEqCUDA.jl -- Julia host shim over libsimplediffeq_cuda (include/simplediffeq_cuda.h).
+#
+# STATUS: UNTESTED.  The build container has no Julia toolchain (`julia` is not installed and
+# there is no network), so this file has never been executed.  It is the binding a maintainer
+# of SciML/SimpleDiffEq.jl would add; INTEGRATION.md walks through it.  The Python package
+# `simplediffeq.jl_b200/api.py` is the same logic in the language that could be tested here.
+#
+# What it does: overloads ensemble solves of the GPUSimple* algorithms so that
+#     solve(EnsembleProblem(prob; prob_func), GPUSimpleTsit5(), EnsembleCUDAB200();
+#           trajectories = N, dt = ..., saveat = ..., save_everystep = ...)
+# evaluates prob_func on the host for i = 1:N, packs u0 / p as structure-of-arrays, makes ONE
+# ccall into the C ABI (all trajectories cross the boundary together) and wraps the raw output
+# into an EnsembleSolution of `build_solution` objects (retcode Default), like the reference's
+# per-trajectory `solve` methods (src/tsit5/gpuatsit5.jl:136-140, :326-329) do.
+module SimpleDiffEqCUDA
+
+using SimpleDiffEq, SciMLBase, StaticArrays
+import SciMLBase: __solve, EnsembleProblem, EnsembleSolution, build_solution, ReturnCode
+
+const libsde = get(ENV, "LIBSIMPLEDIFFEQ_CUDA", "libsimplediffeq_cuda")
+
+# ---- mirror of sde_options_t (field order and types must match the header) ---------------------
+struct SdeOptions
+    alg::Int32
+    dtype::Int32
+    save_mode::Int32
+    layout::Int32
+    compat::Int32
+    reserved::Int32
+    n_traj::Int64
+    t0::Float64
+    tf::Float64
+    dt::Float64
+    abstol::Float64
+    reltol::Float64
+    n_steps::Int64
+    tgrid::Ptr{Cvoid}
+    saveat::Ptr{Cvoid}
+    n_save::Int64
+    max_attempts::Int64
+end
+
+const SDE_SAVE_ENDPOINT, SDE_SAVE_SAVEAT, SDE_SAVE_EVERYSTEP = Int32(0), Int32(1), Int32(2)
+const SDE_LAYOUT_TRAJ_MAJOR, SDE_LAYOUT_SOA = Int32(0), Int32(1)
+
+alg_id(::GPUSimpleTsit5) = Int32(0)
+alg_id(::GPUSimpleATsit5) = Int32(1)
+alg_id(::GPUSimpleRK4) = Int32(2)
+alg_id(::GPUSimpleVern7) = Int32(3)
+alg_id(::GPUSimpleAVern7) = Int32(4)
+alg_id(::GPUSimpleVern9) = Int32(5)
+alg_id(::GPUSimpleAVern9) = Int32(6)
+is_adaptive(alg) = alg isa Union{GPUSimpleATsit5, GPUSimpleAVern7, GPUSimpleAVern9}
+
+"Ensemble algorithm selecting the B200 library; `devices` = CUDA ordinals to shard over."
+struct EnsembleCUDAB200 <: SciMLBase.EnsembleAlgorithm
+    devices::Vector{Cint}
+end
+EnsembleCUDAB200() = EnsembleCUDAB200(Cint[0])
+
+last_error() = unsafe_string(ccall((:sde_last_error, libsde), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("libsimplediffeq_cuda: " * last_error())
+
+# ---- right-hand sides ---------------------------------------------------------------------------
+"A device right-hand side: built-in registry entry or CUDA-C source (NVRTC)."
+struct DeviceRHS
+    handle::Ptr{Cvoid}
+    n_state::Int
+    n_param::Int
+end
+
+function builtin_rhs(name::AbstractString)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sde_system_builtin, libsde), Cint, (Cstring, Ref{Ptr{Cvoid}}), name, h))
+    ns, np = Ref{Cint}(0), Ref{Cint}(0)
+    check(ccall((:sde_system_dims, libsde), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}), h[], ns, np))
+    DeviceRHS(h[], ns[], np[])
+end
+
+"`src` defines `__device__ void rhs(real* du, const real* u, const real* p, real t)`."
+function cuda_rhs(src::AbstractString, n_state::Integer, n_param::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    log = Vector{UInt8}(undef, 16384)
+    rc = ccall((:sde_system_nvrtc, libsde), Cint,
+        (Cstring, Cint, Cint, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t),
+        src, n_state, n_param, h, log, length(log))
+    rc == 0 || error("NVRTC: " * last_error())
+    DeviceRHS(h[], n_state, n_param)
+end
+
+# The ODEProblem's `f` stays an ordinary Julia function (used by the CPU path and by prob_func);
+# the device RHS that implements the same formula is attached through this registry.
+const DEVICE_RHS = IdDict{Any, DeviceRHS}()
+register_device_rhs!(f, rhs::DeviceRHS) = (DEVICE_RHS[f] = rhs)
+
+# ---- the ensemble solve ---------------------------------------------------------------------------
+function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTsit5, GPUSimpleATsit5,
+            GPUSimpleRK4, GPUSimpleVern7, GPUSimpleAVern7, GPUSimpleVern9, GPUSimpleAVern9},
+        ensemblealg::EnsembleCUDAB200;
+        trajectories, dt = alg isa GPUSimpleRK4 ? error("dt is required for this algorithm") : 0.1f0,
+        abstol = 1.0f-6, reltol = 1.0f-3, saveat = nothing, save_everystep = true,
+        layout = SDE_LAYOUT_TRAJ_MAJOR, compat = 0, kwargs...)
+    prob = ensembleprob.prob
+    @assert !SciMLBase.isinplace(prob)
+    T = eltype(prob.u0)
+    T in (Float64, Float32) || error("only Float64 / Float32 states run on the device; use the reference's own method")
+    f = prob.f isa SciMLBase.ODEFunction ? prob.f.f : prob.f
+    rhs = get(DEVICE_RHS, f, nothing)
+    rhs === nothing && error("no device RHS registered for this f (register_device_rhs!)")
+    N, NP, n = rhs.n_state, rhs.n_param, Int(trajectories)
+
+    # prob_func on the host, i = 1:N; only u0 and p may change
+    u0 = Matrix{T}(undef, n, N)          # column-major: u0[i, c] == SoA [c][i]
+    p = Matrix{T}(undef, n, NP)
+    for i in 1:n
+        pi = ensembleprob.prob_func(prob, i, 1)
+        pi.tspan == prob.tspan || error("prob_func may only change u0 and p on the device path")
+        u0[i, :] .= pi.u0
+        NP > 0 && (p[i, :] .= pi.p)
+    end
+
+    t0, tf = T(prob.tspan[1]), T(prob.tspan[2])
+    dtT = T(dt)
+    adaptive = is_adaptive(alg)
+    save_mode = alg isa GPUSimpleRK4 ? SDE_SAVE_EVERYSTEP :
+                saveat !== nothing ? SDE_SAVE_SAVEAT :
+                save_everystep ? SDE_SAVE_EVERYSTEP : SDE_SAVE_ENDPOINT
+    adaptive && save_mode == SDE_SAVE_EVERYSTEP &&
+        error("adaptive save_everystep=true is not provided by the device path yet; pass saveat or save_everystep=false")
+    tgrid = adaptive ? T[] : collect(T, t0:dtT:tf)          # _ts = tspan[1]:dt:tspan[2]
+    sa = saveat === nothing ? T[] : collect(T, saveat)
+    n_steps = adaptive ? 0 : length(tgrid) - 1
+    slots = save_mode == SDE_SAVE_SAVEAT ? length(sa) : save_mode == SDE_SAVE_EVERYSTEP ? n_steps + 1 : 1
+
+    out_u = save_mode == SDE_SAVE_ENDPOINT ? Matrix{T}(undef, n, N) : Array{T}(undef, N, slots, n)  # traj-major
+    out_t = Vector{T}(undef, n)
+    nacc, nrej, ret = zeros(Int32, n), zeros(Int32, n), zeros(Int32, n)
+    GC.@preserve tgrid sa begin
+        opt = Ref(SdeOptions(alg_id(alg), T === Float64 ? 0 : 1, save_mode, layout, compat, 0, n,
+            t0, tf, dtT, T(abstol), T(reltol), n_steps,
+            isempty(tgrid) ? C_NULL : pointer(tgrid), isempty(sa) ? C_NULL : pointer(sa), length(sa), 0))
+        check(ccall((:sde_solve, libsde), Cint,
+            (Ptr{Cvoid}, Ref{SdeOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32},
+                Ptr{Int32}, Ptr{Cint}, Cint),
+            rhs.handle, opt, u0, p, out_u, out_t, nacc, nrej, ret, ensemblealg.devices, length(ensemblealg.devices)))
+        any(==(1), ret) && error("dt<dtmin")            # what the reference throws (gpuatsit5.jl:256)
+        ts_fixed = T[]
+        if !adaptive
+            ts_fixed = Vector{T}(undef, max(slots, 2))
+            nw = Ref{Int64}(0)
+            check(ccall((:sde_fixed_times, libsde), Cint, (Ref{SdeOptions}, Ptr{Cvoid}, Int64, Ref{Int64}),
+                opt, ts_fixed, length(ts_fixed), nw))
+            resize!(ts_fixed, nw[])
+        end
+    end
+
+    SV = SVector{N, T}
+    sols = map(1:n) do i
+        pi = ensembleprob.prob_func(prob, i, 1)
+        if save_mode == SDE_SAVE_ENDPOINT
+            us = [SV(pi.u0), SV(ntuple(c -> out_u[i, c], N))]
+            ts = adaptive ? T[t0, out_t[i]] : ts_fixed
+        else
+            us = collect(reinterpret(SV, vec(view(out_u, :, :, i))))
+            ts = save_mode == SDE_SAVE_SAVEAT ? sa : ts_fixed
+        end
+        build_solution(pi, alg, ts, us; calculate_error = false)   # retcode stays ReturnCode.Default
+    end
+    return EnsembleSolution(sols, 0.0, true)
+end
+
+end # module

@@ -52,7 +52,9 @@ struct RK4Method {
     for (int i = 0; i < N; ++i)
       u[i] = fma(sdt, fma(two, k3[i], fma(two, k2[i], k1[i] + k4[i])), uprev[i]);
   }
+  static constexpr int kNB = 1;
   template <bool> __device__ __forceinline__ void dense_prepare(const T*, const T*, T, T) {}
+  template <bool> __device__ __forceinline__ void dense_combine(const T*, T, const T*, T*) const {}
   template <bool> __device__ __forceinline__ void dense(T, T, const T*, T*) const {}
 };
 
@@ -89,30 +91,126 @@ __device__ __forceinline__ void load_problem(const KArgs<T>& a, i64 traj, T* u, 
 }
 
 // ------------------------------------------------------------------------------------------
-// fixed-step body
-//   SAVE   kSaveEndpoint | kSaveAt | kSaveEveryStep
-//   Q2     reference-exact fixed-step Vern9 dense output (see sde_methods_gen.cuh)
-// Follows src/tsit5/gpuatsit5.jl:86-134, src/rk4/gpurk4.jl:66-85, src/verner/gpuvern7.jl:102-228,
-// src/verner/gpuvern9.jl:100-339.
+// series output writer.
+//   STAGED = false: direct stores in the layout the launch asked for.  Coalesced for kLayoutSoA
+//            (consecutive lanes -> consecutive addresses).
+//   STAGED = true : kLayoutTrajMajor, fixed step.  Each trajectory owns a contiguous row
+//            out_u[traj][slot][c]; a thread storing its own N values would touch 32 different rows
+//            per instruction.  Instead every warp stages S consecutive slots of its 32 trajectories
+//            in shared memory and then writes 32 contiguous runs of S*N elements with consecutive
+//            lanes on consecutive addresses (full 32-byte sectors except at the run ends, which
+//            the neighbouring runs complete while the line is still in L2).
 // ------------------------------------------------------------------------------------------
-template <class Sys, class T, class Method, int SAVE, bool Q2>
+template <class T, int N>
+struct StageCfg {
+#ifndef SDE_STAGE_ELEMS_F64
+#define SDE_STAGE_ELEMS_F64 45   // 4 warps x 32 lanes x 45 x 8 B = 46 080 B  (<= 48 KB: no opt-in needed)
+#define SDE_STAGE_ELEMS_F32 93   // 4 warps x 32 lanes x 93 x 4 B = 47 616 B
+#endif
+  static constexpr int kElems = (sizeof(T) == 8 ? SDE_STAGE_ELEMS_F64 : SDE_STAGE_ELEMS_F32);
+  static constexpr int S = (kElems / N) > 0 ? (kElems / N) : 1;  // slots staged per flush
+  static constexpr int LS = (S * N) | 1;                      // lane stride, odd: conflict-free for 4- and 8-byte words
+  static constexpr int kBytesPerWarp = 32 * LS * (int)sizeof(T);
+};
+
+extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
+
+template <class T, int N, bool STAGED>
+struct SeriesWriter {
+  using Cfg = StageCfg<T, N>;
+  const KArgs<T>& a;
+  i64 traj;
+  bool valid;
+  i64 slot;      // next slot to be written by put()
+  T* buf;        // this warp's staging region
+  int fill;      // slots currently staged
+  i64 slot0;     // slot index of the first staged slot
+  i64 warp_traj0;
+  unsigned lane;
+
+  __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
+      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0) {
+    lane = threadIdx.x & 31u;
+    warp_traj0 = traj - lane;
+    if (STAGED) buf = reinterpret_cast<T*>(sde_dyn_smem) + (threadIdx.x >> 5) * (32 * Cfg::LS);
+  }
+
+  template <bool kFull>
+  __device__ __forceinline__ void flush(int cnt) {
+    __syncwarp();
+    const int per = kFull ? Cfg::S * N : cnt * N;    // elements per trajectory in this flush
+    const int total = 32 * per;
+    T* const row0 = a.out_u + (warp_traj0 * a.n_out + slot0) * N;   // row of the warp's first trajectory
+    const i64 row_stride = a.n_out * N;
+    const int n_valid = (int)((a.n_traj - warp_traj0) < 32 ? (a.n_traj - warp_traj0) : 32);
+#pragma unroll 5
+    for (int k = lane; k < total; k += 32) {
+      const int tr = k / per;
+      const int off = k - tr * per;
+      const T v = buf[tr * Cfg::LS + off];
+      if (tr < n_valid) row0[tr * row_stride + off] = v;
+    }
+    __syncwarp();
+    slot0 += cnt;
+    fill = 0;
+  }
+
+  // all lanes of a warp call put() together with the same slot (fixed-step kernels are uniform)
+  __device__ __forceinline__ void put(const T* v) {
+    if (STAGED) {
+      T* my = buf + lane * Cfg::LS + fill * N;
+#pragma unroll
+      for (int c = 0; c < N; ++c) my[c] = v[c];
+      ++fill;
+      ++slot;
+      if (fill == Cfg::S) flush<true>(Cfg::S);
+    } else {
+      if (valid) put_series<T, N>(a, traj, slot, v);
+      ++slot;
+    }
+  }
+
+  __device__ __forceinline__ void finish() {
+    if (STAGED && fill > 0) flush<false>(fill);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// fixed-step body
+//   SAVE    kSaveEndpoint | kSaveAt | kSaveEveryStep
+//   Q2      reference-exact fixed-step Vern9 dense output (see sde_methods_gen.cuh)
+//   STAGED  shared-memory staged trajectory-major series output (see SeriesWriter)
+// Follows src/tsit5/gpuatsit5.jl:86-134, src/rk4/gpurk4.jl:66-85, src/verner/gpuvern7.jl:102-228,
+// src/verner/gpuvern9.jl:100-339.  The saveat schedule (`while cur_t <= length(ts) && ts[cur_t] <= t`,
+// theta and the b_j(theta) polynomials) is the same for every trajectory of a fixed-step solve;
+// the launcher evaluates it once on the host with the same IEEE operations (sde_api.cu,
+// build_save_plan) and the kernel only does the per-trajectory combination.
+// ------------------------------------------------------------------------------------------
+template <class Sys, class T, class Method, int SAVE, bool Q2, bool STAGED>
 __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP;
   constexpr bool kEnd = MethodTraits<Method>::kTimeIsStepEnd;
-  const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (traj >= a.n_traj) return;
+  i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = traj < a.n_traj;
+  if (!STAGED || SAVE == kSaveEndpoint) {
+    if (!valid) return;
+  }
+  // staged series output: every lane of the warp must reach the cooperative flushes, so lanes past
+  // the end integrate a copy of the last trajectory and never store
+  const i64 src = valid ? traj : a.n_traj - 1;
 
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
-  load_problem<T, N, NP>(a, traj, u, p);
+  load_problem<T, N, NP>(a, src, u, p);
 
   Method m;
   T t = a.t0;
   m.seed(u, p, t);
+  SeriesWriter<T, N, STAGED && SAVE != kSaveEndpoint> w(a, traj, valid);
   int cur = 0;
-  if (SAVE == kSaveEveryStep) put_series<T, N>(a, traj, 0, u);
+  if (SAVE == kSaveEveryStep) w.put(u);
   if (SAVE == kSaveAt) {
-    if (a.n_save > 0 && a.t0 == a.saveat[0]) {   // us[1] = u0 only on exact equality (Q8)
-      put_series<T, N>(a, traj, 0, u);
+    if (a.n_save > 0 && a.plan_step[0] == 0) {   // us[1] = u0 only when tspan[1] == ts[1] exactly (Q8)
+      w.put(u);
       cur = 1;
     }
   }
@@ -124,19 +222,20 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     t = kEnd ? a.tgrid[s] : a.tgrid[s - 1];      // range element, never an accumulated sum
     m.template stages<false>(uprev, u, p, t, dt);
     if (!kEnd) t = t + dt;
-    if (SAVE == kSaveEveryStep) put_series<T, N>(a, traj, s, u);
+    if (SAVE == kSaveEveryStep) w.put(u);
     if (SAVE == kSaveAt) {
       bool prepared = false;
-      while (cur < a.n_save && a.saveat[cur] <= t) {
-        const T savet = a.saveat[cur];
-        const T th = (savet - (t - dt)) / dt;
+      while (cur < a.n_save && (i64)a.plan_step[cur] == s) {
         if (!prepared) {           // extra stages do not depend on theta: once per step
           m.template dense_prepare<Q2>(uprev, p, t, dt);   // time base = advanced t (Q3)
           prepared = true;
         }
+        T b[Method::kNB];
+#pragma unroll
+        for (int j = 0; j < Method::kNB; ++j) b[j] = a.plan_b[(i64)cur * Method::kNB + j];
         T o[N];
-        m.template dense<Q2>(th, dt, uprev, o);
-        put_series<T, N>(a, traj, cur, o);
+        m.template dense_combine<Q2>(b, dt, uprev, o);
+        w.put(o);
         ++cur;
       }
     }
@@ -148,9 +247,10 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
       T nanv[N];
 #pragma unroll
       for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
-      for (; cur < a.n_save; ++cur) put_series<T, N>(a, traj, cur, nanv);
+      for (; cur < a.n_save; ++cur) w.put(nanv);
     }
   }
+  if (SAVE != kSaveEndpoint) w.finish();
 }
 
 // ------------------------------------------------------------------------------------------

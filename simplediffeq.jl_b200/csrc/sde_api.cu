@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -18,6 +19,7 @@
 #include "../../include/simplediffeq_cuda.h"
 #include "device/sde_common.cuh"
 #include "sde_builtin_decl.h"
+#include "sde_interp_host_gen.h"
 
 // ids in the public header and in the device headers must agree
 static_assert((int)sde::kTsit5 == SDE_ALG_TSIT5 && (int)sde::kATsit5 == SDE_ALG_ATSIT5 &&
@@ -61,6 +63,28 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 bool is_adaptive(int alg) { return alg == SDE_ALG_ATSIT5 || alg == SDE_ALG_AVERN7 || alg == SDE_ALG_AVERN9; }
+
+// kernel variant bits (sde_builtin_decl.h)
+bool want_q2(const sde_options_t* o) {
+  return o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT && !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
+}
+bool want_strict(const sde_options_t* o) { return is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER); }
+bool want_staged(const sde_options_t* o) {
+  return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
+}
+// dynamic shared memory of the staged writer: must mirror sde::StageCfg
+// Tuning knob (NVRTC systems only, development): SDE_TUNE_STAGE_ELEMS=<elements staged per lane>
+int tune_stage_elems() {
+  const char* e = getenv("SDE_TUNE_STAGE_ELEMS");
+  return e ? atoi(e) : 0;
+}
+size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
+  int elems = es == 8 ? 45 : 93;
+  if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
+  const int S = std::max(1, elems / n_state);
+  const int LS = (S * n_state) | 1;
+  return (size_t)(block / 32) * 32 * LS * es;
+}
 size_t esize(int dtype) { return dtype == SDE_F64 ? 8 : 4; }
 
 struct Compiled {
@@ -146,7 +170,7 @@ const char* method_name(int alg) {
   }
 }
 
-std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool strict, bool syntax_only) {
+std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool strict, bool staged, bool syntax_only) {
   std::string s;
   s += dtype == SDE_F64 ? "typedef double real;\n" : "typedef float real;\n";
   s += "#include \"sde_kernels.cuh\"\n";
@@ -174,8 +198,8 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
   } else {
     snprintf(buf, sizeof buf,
              "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
-             "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s>(a);\n}\n",
-             kBlock, method_name(alg), save, q2 ? "true" : "false");
+             "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
+             kBlock, method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
   }
   s += buf;
   return s;
@@ -186,9 +210,14 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
   nvrtcResult r = nvrtcCreateProgram(&prog, program.c_str(), "sde_user.cu", sde_embedded_count,
                                      sde_embedded_sources, sde_embedded_names);
   if (r != NVRTC_SUCCESS) return fail(SDE_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+  char tune[96];
+  const int te = tune_stage_elems();
+  snprintf(tune, sizeof tune, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 45);
+  char tune32[96];
+  snprintf(tune32, sizeof tune32, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 93);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo",
-                        "-default-device"};
-  r = nvrtcCompileProgram(prog, 5, opts);
+                        "-default-device", tune, tune32};
+  r = nvrtcCompileProgram(prog, 7, opts);
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
   std::string lg(ls, '\0');
@@ -214,17 +243,15 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
 
 // returns the cache entry (compiled; module loaded only if `load`)
 int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
-  const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
-                  !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
-  const bool strict = is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER);
+  const bool q2 = want_q2(o), strict = want_strict(o), staged = want_staged(o);
   int dev = -1;
   if (load) SDE_CUDA(cudaGetDevice(&dev));
   char key[96];
-  snprintf(key, sizeof key, "%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict);
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict, (int)staged);
   std::lock_guard<std::mutex> lk(sys->mu);
   Compiled& c = sys->cache[key];
   if (c.cubin.empty()) {
-    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, false);
+    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, staged, false);
     int rc = nvrtc_compile(prog, &c.cubin, nullptr);
     if (rc != SDE_OK) { sys->cache.erase(key); return rc; }
   }
@@ -244,10 +271,8 @@ int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const 
 
 int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
   if (sys->builtin) {
-    const bool q2 = o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT &&
-                    !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
-    const bool strict = is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER);
-    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode, (q2 ? 1 : 0) | (strict ? 2 : 0));
+    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode,
+                                     (want_q2(o) ? 1 : 0) | (want_strict(o) ? 2 : 0) | (want_staged(o) ? 4 : 0));
     if (!ki.fn)
       return fail(SDE_ERR_UNSUPPORTED, "no kernel for system %s alg %d dtype %d save_mode %d",
                   sys->name.c_str(), o->alg, o->dtype, o->save_mode);
@@ -255,6 +280,46 @@ int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void*
     return SDE_OK;
   }
   return get_user_kernel(sys, o, load, fn);
+}
+
+// --------------------------------------------------------------------------------------------
+// fixed step + saveat: the schedule of src/tsit5/gpuatsit5.jl:116-127 (`while cur_t <= length(ts) &&
+// ts[cur_t] <= t`, theta = (savet - (t - dt))/dt, b(theta) by @evalpoly) does not depend on the
+// trajectory.  Evaluate it once here, in T, with the same IEEE operations the device would use.
+// --------------------------------------------------------------------------------------------
+template <class T>
+void build_save_plan(int alg, const T* tgrid, int64_t n_steps, T t0, T dt, const T* saveat, int64_t n_save,
+                     std::vector<int>* step, std::vector<T>* b, int* nb_out) {
+  const double* poly = nullptr;
+  const int* len = nullptr;
+  int nb = 0, deg = 0;
+  switch (alg) {
+    case SDE_ALG_TSIT5: poly = &sde_host::kTsit5Poly[0][0]; len = sde_host::kTsit5Len; nb = sde_host::kTsit5NB; deg = sde_host::kTsit5Deg; break;
+    case SDE_ALG_VERN7: poly = &sde_host::kVern7Poly[0][0]; len = sde_host::kVern7Len; nb = sde_host::kVern7NB; deg = sde_host::kVern7Deg; break;
+    default: poly = &sde_host::kVern9Poly[0][0]; len = sde_host::kVern9Len; nb = sde_host::kVern9NB; deg = sde_host::kVern9Deg; break;
+  }
+  *nb_out = nb;
+  step->assign((size_t)n_save, (int)std::min<int64_t>(n_steps + 1, 0x7fffffff));   // "never reached"
+  b->assign((size_t)n_save * nb, (T)0);
+  int64_t cur = 0;
+  if (n_save > 0 && t0 == saveat[0]) { (*step)[0] = 0; cur = 1; }
+  for (int64_t s = 1; s <= n_steps && cur < n_save; ++s) {
+    volatile T tv = tgrid[s - 1];
+    tv = tv + dt;                                   // t = _ts[i-1]; t += dt
+    const T t = tv;
+    while (cur < n_save && saveat[cur] <= t) {
+      volatile T tm = t - dt;
+      const T th = (saveat[cur] - tm) / dt;
+      for (int j = 0; j < nb; ++j) {
+        const double* c = poly + (size_t)j * deg;
+        T acc = (T)c[len[j] - 1];
+        for (int d = len[j] - 2; d >= 0; --d) acc = std::fma(th, acc, (T)c[d]);
+        (*b)[(size_t)cur * nb + j] = acc;
+      }
+      (*step)[(size_t)cur] = (int)s;
+      ++cur;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -284,28 +349,46 @@ int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const vo
   a.out_t = adaptive ? (T*)d_out_t : nullptr;
   a.naccept = d_nacc; a.nreject = d_nrej; a.retcode = d_ret;
 
-  // small per-call device constants: time grid, saveat, queue head
+  // small per-call device constants: queue head, time grid, saveat (adaptive) or save plan (fixed)
   const size_t ng = adaptive ? 0 : (size_t)o->n_steps + 1;
   const size_t ns = (size_t)a.n_save;
-  const size_t bytes = (ng + ns) * sizeof(T) + 16;
+  std::vector<T> tg(ng);
+  if (ng) {
+    if (o->tgrid) memcpy(tg.data(), o->tgrid, ng * sizeof(T));
+    else for (size_t k = 0; k < ng; ++k) tg[k] = (T)o->t0 + (T)((T)k * (T)o->dt);
+  }
+  std::vector<int> plan_step;
+  std::vector<T> plan_b;
+  int nb = 0;
+  if (!adaptive && ns) {
+    if (o->n_steps >= 0x7ffffffeLL) return fail(SDE_ERR_INVALID, "n_steps too large for saveat");
+    build_save_plan<T>(o->alg, tg.data(), o->n_steps, (T)o->t0, (T)o->dt, (const T*)o->saveat, o->n_save,
+                       &plan_step, &plan_b, &nb);
+  }
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t off_grid = 16;
+  const size_t off_save = off_grid + up16(ng * sizeof(T));
+  const size_t off_pstep = off_save + up16((adaptive ? ns : 0) * sizeof(T));
+  const size_t off_pb = off_pstep + up16(plan_step.size() * sizeof(int));
+  const size_t bytes = off_pb + up16(plan_b.size() * sizeof(T));
   char* scratch = nullptr;
   SDE_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
   SDE_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
   a.queue = (sde::u64*)scratch;
-  T* d_grid = (T*)(scratch + 16);
-  std::vector<T> host((ng + ns));
+  // pageable sources are staged by the runtime before cudaMemcpyAsync returns, so the vectors may die
   if (ng) {
-    if (o->tgrid) memcpy(host.data(), o->tgrid, ng * sizeof(T));
-    else for (size_t k = 0; k < ng; ++k) host[k] = (T)o->t0 + (T)((T)k * (T)o->dt);
-    a.tgrid = d_grid;
+    SDE_CUDA(cudaMemcpyAsync(scratch + off_grid, tg.data(), ng * sizeof(T), cudaMemcpyHostToDevice, st));
+    a.tgrid = (const T*)(scratch + off_grid);
   }
-  if (ns) {
-    memcpy(host.data() + ng, o->saveat, ns * sizeof(T));
-    a.saveat = d_grid + ng;
+  if (adaptive && ns) {
+    SDE_CUDA(cudaMemcpyAsync(scratch + off_save, o->saveat, ns * sizeof(T), cudaMemcpyHostToDevice, st));
+    a.saveat = (const T*)(scratch + off_save);
   }
-  if (ng + ns) {
-    SDE_CUDA(cudaMemcpyAsync(d_grid, host.data(), (ng + ns) * sizeof(T), cudaMemcpyHostToDevice, st));
-    // the pageable source is staged by the runtime before the call returns, so `host` may die
+  if (!plan_step.empty()) {
+    SDE_CUDA(cudaMemcpyAsync(scratch + off_pstep, plan_step.data(), plan_step.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SDE_CUDA(cudaMemcpyAsync(scratch + off_pb, plan_b.data(), plan_b.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    a.plan_step = (const int*)(scratch + off_pstep);
+    a.plan_b = (const T*)(scratch + off_pb);
   }
 
   if (o->n_traj > 0) {
@@ -322,12 +405,17 @@ int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const vo
       if (full > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
       grid = (unsigned)full;
     }
+    size_t smem = 0;
+    if (want_staged(o)) {
+      smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
+      if (smem > 48 * 1024)
+        SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     void* params[] = {&a};
-    SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, 0, st));
+    SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, smem, st));
     g_launches.fetch_add(1);
   }
   SDE_CUDA(cudaFreeAsync(scratch, st));
-  (void)sys;
   return SDE_OK;
 }
 
@@ -467,7 +555,7 @@ int sde_system_nvrtc(const char* src, int n_state, int n_param, sde_system_t* ou
   // syntax check now (both element types must compile), kernels are built lazily
   for (int dtype = 0; dtype < 2; ++dtype) {
     std::string lg;
-    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, false, true), nullptr, &lg);
+    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, false, false, true), nullptr, &lg);
     if (rc != SDE_OK) {
       if (log && log_len) { strncpy(log, lg.c_str(), log_len - 1); log[log_len - 1] = '\0'; }
       delete s;

@@ -11,9 +11,9 @@
 
 namespace sde {
 
-template <class Sys, class T, class Method, int SAVE, bool Q2>
+template <class Sys, class T, class Method, int SAVE, bool Q2, bool STAGED>
 __global__ void __launch_bounds__(SDE_BLOCK) fixed_kernel(const __grid_constant__ KArgs<T> a) {
-  fixed_body<Sys, T, Method, SAVE, Q2>(a);
+  fixed_body<Sys, T, Method, SAVE, Q2, STAGED>(a);
 }
 
 template <class Sys, class T, class Method, int SAVE, bool kV9, bool kStrict>
@@ -21,13 +21,22 @@ __global__ void __launch_bounds__(SDE_BLOCK) adaptive_kernel(const __grid_consta
   adaptive_body<Sys, T, Method, SAVE, kV9, kStrict>(a);
 }
 
+// staged variants exist only for the series modes
+template <class Sys, class T, class M, int S, bool Q>
+inline KernelInfo pick_fixed(bool staged) {
+  if constexpr (S != kSaveEndpoint) {
+    if (staged) return KernelInfo{(const void*)&fixed_kernel<Sys, T, M, S, Q, true>, false};
+  }
+  return KernelInfo{(const void*)&fixed_kernel<Sys, T, M, S, Q, false>, false};
+}
+
 template <class Sys, class T>
-inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict) {
+inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool staged) {
   using TS = Tsit5Method<Sys, T>;
   using RK = RK4Method<Sys, T>;
   using V7 = Vern7Method<Sys, T>;
   using V9 = Vern9Method<Sys, T>;
-#define SDE_FIXED(M, S, Q) KernelInfo{(const void*)&fixed_kernel<Sys, T, M, S, Q>, false}
+#define SDE_FIXED(M, S, Q) pick_fixed<Sys, T, M, S, Q>(staged)
 #define SDE_ADAPT(M, S, V)                                                       \
   (strict ? KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, true>, true} \
           : KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, false>, true})
@@ -71,9 +80,9 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict) {
 
 template <class Sys>
 inline KernelInfo lookup_kernel(int alg, int dtype, int save, int variant) {
-  const bool q2 = (variant & 1) != 0, strict = (variant & 2) != 0;
-  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2, strict)
-                    : lookup_kernel_t<Sys, float>(alg, save, q2, strict);
+  const bool q2 = (variant & 1) != 0, strict = (variant & 2) != 0, staged = (variant & 4) != 0;
+  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2, strict, staged)
+                    : lookup_kernel_t<Sys, float>(alg, save, q2, strict, staged);
 }
 
 }  // namespace sde

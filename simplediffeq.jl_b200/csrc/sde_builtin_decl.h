@@ -9,7 +9,8 @@ struct KernelInfo {
 };
 }  // namespace sde
 
-// variant: bit 0 = reference-exact fixed-step Vern9 dense output (Q2), bit 1 = strict controller
+// variant: bit 0 = reference-exact fixed-step Vern9 dense output (Q2), bit 1 = strict controller,
+//          bit 2 = shared-memory staged trajectory-major series output (fixed step)
 typedef sde::KernelInfo (*sde_builtin_lookup_fn)(int alg, int dtype, int save, int variant);
 
 sde::KernelInfo sde_lookup_lorenz(int, int, int, int);

@@ -332,13 +332,19 @@ def emit_method(sp, refnote):
             o.append("    Sys::rhs(k%d, tmp, p, fma(C.%s, dt, tx));\n" % (s, time))
     o.append("  }\n")
     # ---- dense output
-    o.append("\n  // dense output at theta in [0,1]: out = uprev + dt * sum_j b_j(theta) k_j\n")
-    o.append("  template <bool kQ2>\n")
-    o.append("  __device__ __forceinline__ void dense(T th, T dt, const T* uprev, T* out) const {\n")
+    nb = len(sp["polys"])
+    o.append("\n  // dense-output weights b_j(theta) (Horner with fma == @evalpoly), in the reference's order\n")
+    o.append("  static constexpr int kNB = %d;\n" % nb)
+    o.append("  __device__ __forceinline__ static void bthetas(T th, T* b) {\n")
     o.append("    const %sCoef<T>& C = Coefs<T>::%s();\n" % (name, low))
-    for j, coefs in sp["polys"]:
-        o.append("    const T b%d = %s;\n" % (j, horner(coefs)))
-    terms = [("b%d" % j, j) for j, _ in sp["polys"]]
+    for idx, (j, coefs) in enumerate(sp["polys"]):
+        o.append("    b[%d] = %s;\n" % (idx, horner(coefs)))
+    o.append("  }\n")
+    o.append("\n  // dense output: out = uprev + dt * sum_j b_j k_j   (b from bthetas(); fixed-step kernels get\n"
+             "  // them precomputed by the host because theta is the same for every trajectory)\n")
+    o.append("  template <bool kQ2>\n")
+    o.append("  __device__ __forceinline__ void dense_combine(const T* b, T dt, const T* uprev, T* out) const {\n")
+    terms = [("b[%d]" % idx, j) for idx, (j, _) in enumerate(sp["polys"])]
 
     def kn2(j, q2):
         if q2 and name == "Vern9" and 8 <= j <= 15:
@@ -353,7 +359,11 @@ def emit_method(sp, refnote):
     else:
         o.append("#pragma unroll\n    for (int i = 0; i < N; ++i)\n      out[i] = fma(dt, %s, uprev[i]);\n"
                  % fold(terms, coef=lambda n: n))
-    o.append("  }\n};\n\n")
+    o.append("  }\n")
+    o.append("  template <bool kQ2>\n")
+    o.append("  __device__ __forceinline__ void dense(T th, T dt, const T* uprev, T* out) const {\n"
+             "    T b[kNB];\n    bthetas(th, b);\n    dense_combine<kQ2>(b, dt, uprev, out);\n  }\n")
+    o.append("};\n\n")
     return "".join(o)
 
 
@@ -374,6 +384,30 @@ def emit_methods(specs):
     return "".join(o)
 
 
+def emit_host_interp(ts, v, specs):
+    """Plain C++ (host) copy of the dense-output polynomials: the launcher precomputes b_j(theta) of
+    every save point of a fixed-step solve (theta does not depend on the trajectory)."""
+    vals = {"Tsit5": dict(ts),
+            "Vern7": dict(v["Vern7InterpolationCoefficients"]),
+            "Vern9": dict(v["Vern9InterpolationCoefficients"])}
+    o = [HDR]
+    o.append("// Host copy of the dense-output polynomial coefficients (ascending powers of theta, zero-padded).\n"
+             "// b_j(theta) = Horner with fma, exactly like the device code / the reference's @evalpoly.\n"
+             "#pragma once\nnamespace sde_host {\n\n")
+    for sp in specs:
+        name = sp["name"]
+        deg = max(len(c) for _, c in sp["polys"])
+        o.append("static const int k%sNB = %d, k%sDeg = %d;\n" % (name, len(sp["polys"]), name, deg))
+        o.append("static const double k%sPoly[%d][%d] = {\n" % (name, len(sp["polys"]), deg))
+        for j, coefs in sp["polys"]:
+            row = [0.0 if c is None else vals[name][c] for c in coefs] + [0.0] * (deg - len(coefs))
+            o.append("  {" + ", ".join(lit(x) for x in row) + "},\n")
+        o.append("};\n")
+        o.append("static const int k%sLen[%d] = {%s};\n\n" % (name, len(sp["polys"]), ", ".join(str(len(c)) for _, c in sp["polys"])))
+    o.append("}  // namespace sde_host\n")
+    return "".join(o)
+
+
 def main():
     ts = parse_tsit5()
     v = parse_verner()
@@ -382,6 +416,7 @@ def main():
         os.path.join(ROOT, "oracle/tableau_named.hpp"): emit_oracle(ts, v),
         os.path.join(PKG, "csrc/device/sde_tableaus_gen.cuh"): emit_device_tables(ts, v),
         os.path.join(PKG, "csrc/device/sde_methods_gen.cuh"): emit_methods(specs),
+        os.path.join(PKG, "csrc/sde_interp_host_gen.h"): emit_host_interp(ts, v, specs),
     }
     for path, text in outs.items():
         os.makedirs(os.path.dirname(path), exist_ok=True)
