@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 #pragma unroll
     for (int r = 0; r < 16; ++r)
 #pragma unroll
-      for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+      for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, x[c]);   // one register + one constant-bank operand,
+                                                                     // like the integrator's tableau FMAs
   }
   T s = 0;
 #pragma unroll
@@ -40,7 +41,7 @@ int probe(double* tflops, double* ms_out) {
   double best = 0, best_ms = 0;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0);
-    fma_peak_kernel<T, CHAINS><<<blocks, threads>>>(d, iters, (T)0.999999, (T)1e-6);
+    fma_peak_kernel<T, CHAINS><<<blocks, threads>>>(d, iters, (T)1e-9, (T)1e-6);
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return SDE_ERR_CUDA; }
     float ms = 0;

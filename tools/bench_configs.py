@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""All five BASELINE.json configs on one GPU (device-resident, CUDA-event timed, best of reps).
+Writes one JSON object per line.  The contract benchmark is bench.py (config 2 = configs[1])."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import simplediffeq_b200 as S
+from simplediffeq_b200 import _lib
+
+DEV = torch.device("cuda:0")
+PIPE64 = 148 * 64 * 1.965e9
+HBM = 6555.2
+DT0 = float(np.float32(0.1))
+
+
+def lorenz(n, dtype=torch.float64):
+    u0 = torch.zeros(3, n, dtype=dtype, device=DEV); u0[0] = 1
+    p = torch.empty(3, n, dtype=dtype, device=DEV); p[0] = 10; p[2] = 8.0 / 3.0
+    p[1] = (21.0 * torch.arange(n, dtype=torch.float64, device=DEV) / max(n - 1, 1)).to(dtype)
+    return u0, p
+
+
+def vdp(n, shuffled):
+    u0 = torch.zeros(2, n, dtype=torch.float64, device=DEV); u0[0] = 2
+    idx = torch.arange(n, dtype=torch.int64, device=DEV)
+    if shuffled:
+        idx = (idx * 2654435761) % n
+    p = (0.1 + 49.9 * idx.to(torch.float64) / max(n - 1, 1)).reshape(1, n).contiguous()
+    return u0, p
+
+
+def timed(fn, reps=3):
+    best, out = 1e30, None
+    for r in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        if r > 0:
+            best = min(best, e0.elapsed_time(e1))
+    return best, out
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def adaptive(name, sysm, alg, u0, p, tspan, tol, instr_per_attempt, compat=0):
+    ms, out = timed(lambda: S.solve_device(sysm, alg, u0, p, tspan, dt=DT0, abstol=tol, reltol=tol, compat=compat, sync=False))
+    acc = int(out["naccept"].sum().item()); rej = int(out["nreject"].sum().item())
+    na = out["naccept"].to(torch.float64)
+    emit(config=name, alg=type(alg).__name__, n=u0.shape[1], tol=tol, compat=compat, ms=ms,
+         accepted_steps_per_s=acc / ms * 1e3, attempts_per_s=(acc + rej) / ms * 1e3,
+         naccept_min=int(na.min().item()), naccept_mean=float(na.mean().item()), naccept_max=int(na.max().item()),
+         reject_frac=rej / (acc + rej),
+         fp64_pipe_frac_est=(acc + rej) / ms * 1e3 * instr_per_attempt / PIPE64,
+         failed=int((out["retcode"] != 0).sum().item()))
+
+
+def main():
+    print(torch.cuda.get_device_name(0), file=sys.stderr)
+    tf64, _ = _lib.probe_fma_peak(_lib.SDE_F64); tf32, _ = _lib.probe_fma_peak(_lib.SDE_F32)
+    emit(config="probe", fp64_fma_tflops=tf64, fp32_fma_tflops=tf32)
+    L = S.systems.lorenz
+    # config 1: 10 k Lorenz sweep, ATsit5 tol 1e-8 (the reference's CPU-runnable case)
+    u0, p = lorenz(10_000)
+    adaptive("1: Lorenz 10k ATsit5 tol 1e-8", L, S.GPUSimpleATsit5(), u0, p, (0.0, 10.0), 1e-8, 236)
+    u0, p = lorenz(1 << 20)
+    adaptive("1b: Lorenz 1Mi ATsit5 tol 1e-8", L, S.GPUSimpleATsit5(), u0, p, (0.0, 10.0), 1e-8, 236)
+    adaptive("1b strict controller", L, S.GPUSimpleATsit5(), u0, p, (0.0, 10.0), 1e-8, 236, compat=2)
+    # config 2: fixed Tsit5 10 M, FP64 and FP32
+    for dtype, nm in ((torch.float64, "f64"), (torch.float32, "f32")):
+        u0, p = lorenz(10_000_000, dtype)
+        out = torch.empty_like(u0)
+        ms, _ = timed(lambda: S.solve_device(L, S.GPUSimpleTsit5(), u0, p, (0.0, 10.0), dt=1e-3, out=out, stats=False, sync=False), reps=2)
+        sps = 10_000_000 * 10_000 / ms * 1e3
+        emit(config="2: Lorenz 10M Tsit5 fixed dt=1e-3 " + nm, ms=ms, steps_per_s=sps, flop_frac=sps * 190 / (PIPE64 * 2 * (1 if nm == "f64" else 2)),
+             pipe_frac=sps * 127 / (PIPE64 * (1 if nm == "f64" else 2)))
+        del u0, p, out
+    # other fixed-step methods, 1 Mi trajectories
+    u0, p = lorenz(1 << 20)
+    for alg, instr in ((S.GPUSimpleRK4(), 55), (S.GPUSimpleVern7(), 208), (S.GPUSimpleVern9(), 391)):
+        ms, _ = timed(lambda: S.solve_device(L, alg, u0, p, (0.0, 10.0), dt=1e-3, stats=False, sync=False), reps=2)
+        sps = (1 << 20) * 10_000 / ms * 1e3
+        emit(config="fixed " + type(alg).__name__ + " 1Mi dt=1e-3 f64", ms=ms, steps_per_s=sps, pipe_frac=sps * instr / PIPE64)
+    # config 3: Van der Pol 1 Mi, ATsit5 tol 1e-6, sorted and shuffled
+    for sh in (False, True):
+        u0, p = vdp(1 << 20, sh)
+        adaptive("3: VdP 1Mi ATsit5 tol 1e-6 " + ("shuffled" if sh else "sorted"), S.systems.vanderpol, S.GPUSimpleATsit5(), u0, p, (0.0, 20.0), 1e-6, 170)
+    # config 4: AVern9 1 M tol 1e-12
+    u0, p = lorenz(1_000_000)
+    adaptive("4: Lorenz 1M AVern9 tol 1e-12", L, S.GPUSimpleAVern9(), u0, p, (0.0, 10.0), 1e-12, 520)
+    adaptive("4b: Lorenz 1M AVern7 tol 1e-10", L, S.GPUSimpleAVern7(), u0, p, (0.0, 10.0), 1e-10, 320)
+    # config 5: 4 M Lorenz, Tsit5 + saveat 0:0.01:10
+    n = 4_000_000
+    u0, p = lorenz(n)
+    saveat = S.jl_range(0.0, 0.01, 10.0)
+    for dt in (0.1, 0.01):
+        for layout, nm in ((1, "soa"), (0, "traj_major_staged")):
+            out = torch.empty((n, 1001, 3) if layout == 0 else (1001, 3, n), dtype=torch.float64, device=DEV)
+            ms, r = timed(lambda: S.solve_device(L, S.GPUSimpleTsit5(), u0, p, (0.0, 10.0), dt=dt, saveat=saveat, save_mode=1, layout=layout, out=out, stats=False, sync=False), reps=1)
+            gbs = n * 24072 / ms / 1e6
+            emit(config="5: Lorenz 4M Tsit5 saveat=0:0.01:10 dt=%g %s" % (dt, nm), ms=ms, hbm_gbs=gbs, hbm_frac=gbs / HBM,
+                 steps_per_s=n * r["n_steps"] / ms * 1e3, bytes_per_traj=24072)
+            del out
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
