@@ -8,6 +8,7 @@
  *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleTsit5;  saveat, save_everystep, dt)                 src/tsit5/gpuatsit5.jl:55-147
  *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleATsit5; dt, saveat, save_everystep, abstol, reltol) src/tsit5/gpuatsit5.jl:205-336
  *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleRK4;    dt)                                         src/rk4/gpurk4.jl:53-98
+ *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleEuler;  dt)                                         src/euler/gpueuler.jl:53-90
  *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleVern7 / GPUSimpleAVern7; ...)                       src/verner/gpuvern7.jl:55-242, :300-536
  *       DiffEqBase.solve(prob::ODEProblem, alg::GPUSimpleVern9 / GPUSimpleAVern9; ...)                       src/verner/gpuvern9.jl:55-353, :411-779
  *     called once per trajectory by SciMLBase's ensemble driver (batch_func) in the reference; here
@@ -61,7 +62,8 @@ enum {
   SDE_ALG_VERN7 = 3,  /* GPUSimpleVern7   fixed step  */
   SDE_ALG_AVERN7 = 4, /* GPUSimpleAVern7  adaptive    */
   SDE_ALG_VERN9 = 5,  /* GPUSimpleVern9   fixed step  */
-  SDE_ALG_AVERN9 = 6  /* GPUSimpleAVern9  adaptive    */
+  SDE_ALG_AVERN9 = 6, /* GPUSimpleAVern9  adaptive    */
+  SDE_ALG_EULER = 7   /* GPUSimpleEuler   fixed step, always saves every step (src/euler/gpueuler.jl:53-90) */
 };
 
 enum { SDE_F64 = 0, SDE_F32 = 1 };
@@ -70,8 +72,9 @@ enum { SDE_F64 = 0, SDE_F32 = 1 };
 enum {
   SDE_SAVE_ENDPOINT = 0,  /* saveat === nothing && save_everystep = false : final state only */
   SDE_SAVE_SAVEAT = 1,    /* saveat = [...] : dense output at the given times */
-  SDE_SAVE_EVERYSTEP = 2  /* saveat === nothing && save_everystep = true (fixed-step algorithms):
-                             n_steps + 1 states, slot 0 = u0 */
+  SDE_SAVE_EVERYSTEP = 2  /* saveat === nothing && save_everystep = true.  Fixed step: n_steps + 1 states,
+                             slot 0 = u0.  Adaptive: slot 0 = u0, slot k = state after the k-th accepted step,
+                             at most opt->out_capacity slots per trajectory (see sde_solve) */
 };
 
 /* layout of series outputs (SAVEAT / EVERYSTEP); n_out = slots per trajectory */
@@ -84,7 +87,9 @@ enum {
 enum {
   SDE_RET_DEFAULT = 0,  /* ReturnCode.Default */
   SDE_RET_DTMIN = 1,    /* the reference would throw error("dt<dtmin") */
-  SDE_RET_MAXITERS = 2  /* max_attempts exhausted (no counterpart in the reference) */
+  SDE_RET_MAXITERS = 2, /* max_attempts exhausted (no counterpart in the reference) */
+  SDE_RET_OUTPUT_FULL = 3 /* adaptive SDE_SAVE_EVERYSTEP: the trajectory took more than out_capacity - 1 accepted
+                             steps; the first out_capacity states are stored, naccept tells how many are needed */
 };
 
 /* compat flags: 0 = reproduce the reference exactly, including its quirks */
@@ -118,6 +123,7 @@ typedef struct sde_options {
   const void* saveat; /* SDE_SAVE_SAVEAT: HOST array of n_save times in dtype */
   int64_t n_save;
   int64_t max_attempts; /* adaptive: 0 = unlimited like the reference */
+  int64_t out_capacity; /* adaptive SDE_SAVE_EVERYSTEP: slots per trajectory in out_u / out_t (>= 1) */
 } sde_options_t;
 
 /* ---- library / device ------------------------------------------------------------------- */
@@ -149,9 +155,13 @@ SDE_API int sde_system_prepare(sde_system_t sys, const sde_options_t* opt);
 /* u0: [n_state][n_traj] (SoA), p: [n_param][n_traj] (SoA), HOST memory (pinned or pageable).
  * out_u: ENDPOINT -> [n_state][n_traj] (SoA final states)
  *        SAVEAT   -> n_out = n_save slots per trajectory, layout per opt->layout
- *        EVERYSTEP-> n_out = n_steps + 1 slots per trajectory
+ *        EVERYSTEP-> fixed step: n_out = n_steps + 1 slots per trajectory; adaptive: n_out = out_capacity
+ *                    slots, of which min(naccept + 1, n_out) are written (run SDE_SAVE_ENDPOINT first to
+ *                    learn naccept when no bound is known: the step sequence is deterministic)
  *        series slots that the reference would leave `undef` are NaN.
- * out_t: adaptive: [n_traj] final time of each trajectory (== tf unless retcode != 0); may be NULL.
+ * out_t: adaptive ENDPOINT / SAVEAT: [n_traj] final time of each trajectory (== tf unless retcode != 0);
+ *        adaptive EVERYSTEP: the time of every stored slot, same layout as out_u without the component
+ *        axis ([n_traj][n_out] or [n_out][n_traj]); may be NULL.
  *        fixed step: ignored (times are trajectory independent: see sde_fixed_times).
  * naccept/nreject/retcode: [n_traj] int32, each may be NULL.
  * devices/n_dev: CUDA device ordinals to shard over by contiguous trajectory ranges, one host

@@ -38,6 +38,7 @@ struct SdeOptions
     saveat::Ptr{Cvoid}
     n_save::Int64
     max_attempts::Int64
+    out_capacity::Int64
 end
 
 const SDE_SAVE_ENDPOINT, SDE_SAVE_SAVEAT, SDE_SAVE_EVERYSTEP = Int32(0), Int32(1), Int32(2)
@@ -138,7 +139,7 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTs
     GC.@preserve tgrid sa begin
         opt = Ref(SdeOptions(alg_id(alg), T === Float64 ? 0 : 1, save_mode, layout, compat, 0, n,
             t0, tf, dtT, T(abstol), T(reltol), n_steps,
-            isempty(tgrid) ? C_NULL : pointer(tgrid), isempty(sa) ? C_NULL : pointer(sa), length(sa), 0))
+            isempty(tgrid) ? C_NULL : pointer(tgrid), isempty(sa) ? C_NULL : pointer(sa), length(sa), 0, 0))
         check(ccall((:sde_solve, libsde), Cint,
             (Ptr{Cvoid}, Ref{SdeOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32},
                 Ptr{Int32}, Ptr{Cint}, Cint),

@@ -211,7 +211,7 @@ template <int NN> thread_local void* UserSys<NN>::fn = nullptr;
 // per-trajectory job description
 // ------------------------------------------------------------------------------------
 enum { SAVE_ENDPOINT = 0, SAVE_SAVEAT = 1, SAVE_EVERYSTEP = 2 };
-enum { ALG_TSIT5 = 0, ALG_ATSIT5 = 1, ALG_RK4 = 2, ALG_VERN7 = 3, ALG_AVERN7 = 4, ALG_VERN9 = 5, ALG_AVERN9 = 6 };
+enum { ALG_TSIT5 = 0, ALG_ATSIT5 = 1, ALG_RK4 = 2, ALG_VERN7 = 3, ALG_AVERN7 = 4, ALG_VERN9 = 5, ALG_AVERN9 = 6, ALG_EULER = 7 };
 enum { RET_DEFAULT = 0, RET_DTMIN = 1, RET_MAXITERS = 2 };
 enum { COMPAT_FIX_VERN9_INTERP = 1,
        // test-only: return the neighbouring floating-point number from the controller's first pow call, to
@@ -453,6 +453,28 @@ void solve_rk4(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O
     //      -> muladd(dt*sixth, muladd(2,k3, muladd(2,k2, k1+k4)), uprev)
     u = muladd(dt * sixth, muladd(two, k3, muladd(two, k2, add(k1, k4))), uprev);
     if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);              // :84 us[i] = u ; ts[i]
+  }
+  if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
+  O.n = slot;
+  O.naccept = (int32_t)J.n_steps; O.nreject = 0; O.retcode = RET_DEFAULT;
+}
+
+// ---- GPUSimpleEuler: src/euler/gpueuler.jl:53-90  (always saves every step, like RK4)
+template <class Sys, class T>
+void solve_euler(const Job<T>& J, Vec<T, Sys::N> u0, const T* p, Out<T, Sys::N>& O) {
+  constexpr int N = Sys::N;
+  using V = Vec<T, N>;
+  T dt = J.dt;
+  int64_t slot = 0;
+  if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u0, J.tgrid ? J.tgrid[0] : J.t0, J.max_out);  // :68 us[1] = u0
+  V u = u0;
+  T t = J.t0;
+  for (int64_t i = 1; i <= J.n_steps; ++i) {                                        // :71
+    V uprev = u;
+    t = J.tgrid[i];                                                                 // :73  t = ts[i]
+    V k1 = Sys::f(u, p, t);                                                         // :74
+    u = muladd(dt, k1, uprev);                                                      // :75  uprev + dt*k1
+    if (J.save_mode == SAVE_EVERYSTEP) O.put(slot++, u, t, J.max_out);              // :76
   }
   if (J.save_mode == SAVE_ENDPOINT) { O.put(0, u, t, J.max_out); slot = 1; }
   O.n = slot;
@@ -829,6 +851,7 @@ void run_range(const EnsembleArgs& A, int64_t lo, int64_t hi) {
       case ALG_AVERN7: solve_avern7<Sys, T>(J, u, p, O); break;
       case ALG_VERN9: solve_vern9<Sys, T>(J, u, p, O); break;
       case ALG_AVERN9: solve_avern9<Sys, T>(J, u, p, O); break;
+      case ALG_EULER: solve_euler<Sys, T>(J, u, p, O); break;
     }
     if (A.out_n) A.out_n[i] = O.n;
     if (A.naccept) A.naccept[i] = O.naccept;
@@ -903,7 +926,7 @@ int oracle_solve(int system, int alg, int dtype, int64_t n_traj, const void* u0,
   A.retcode = retcode; A.n_threads = n_threads; A.user_fn = user_fn;
   { int ns = 0, np = 0; if (system == SYS_USER) np = user_n_param; else if (oracle_system_dims(system, &ns, &np)) return -1; A.n_param = np; }
   if (A.n_param > 8) return -3;
-  if (alg < 0 || alg > 6) return -4;
+  if (alg < 0 || alg > 7) return -4;
   switch (system) {
     case SYS_LORENZ: return run_sys<Lorenz>(A);
     case SYS_VANDERPOL: return run_sys<VanDerPol>(A);

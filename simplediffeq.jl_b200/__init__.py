@@ -5,12 +5,12 @@ include/simplediffeq_cuda.h (libsimplediffeq_cuda.so, built in-tree by build.py)
 Import as `simplediffeq_b200` (see simplediffeq_b200.py at the repository root)."""
 from . import _lib
 from .api import (CudaRHS, EnsembleProblem, EnsembleSolution, GPUSimpleATsit5, GPUSimpleAVern7,
-                  GPUSimpleAVern9, GPUSimpleRK4, GPUSimpleTsit5, GPUSimpleVern7, GPUSimpleVern9,
+                  GPUSimpleAVern9, GPUSimpleEuler, GPUSimpleRK4, GPUSimpleTsit5, GPUSimpleVern7, GPUSimpleVern9,
                   ODEProblem, ODESolution, System, builtin_system, remake, solve, solve_arrays,
                   solve_device, systems)
 from .jlrange import JuliaRange, jl_range
 
 __all__ = ["CudaRHS", "EnsembleProblem", "EnsembleSolution", "GPUSimpleATsit5", "GPUSimpleAVern7",
-           "GPUSimpleAVern9", "GPUSimpleRK4", "GPUSimpleTsit5", "GPUSimpleVern7", "GPUSimpleVern9",
+           "GPUSimpleAVern9", "GPUSimpleEuler", "GPUSimpleRK4", "GPUSimpleTsit5", "GPUSimpleVern7", "GPUSimpleVern9",
            "ODEProblem", "ODESolution", "System", "builtin_system", "remake", "solve", "solve_arrays",
            "solve_device", "systems", "JuliaRange", "jl_range"]

@@ -12,11 +12,11 @@ LIB_PATH = os.path.join(HERE, "libsimplediffeq_cuda.so")
 # ids of include/simplediffeq_cuda.h
 SDE_OK = 0
 ALG_IDS = dict(GPUSimpleTsit5=0, GPUSimpleATsit5=1, GPUSimpleRK4=2, GPUSimpleVern7=3,
-               GPUSimpleAVern7=4, GPUSimpleVern9=5, GPUSimpleAVern9=6)
+               GPUSimpleAVern7=4, GPUSimpleVern9=5, GPUSimpleAVern9=6, GPUSimpleEuler=7)
 SDE_F64, SDE_F32 = 0, 1
 SAVE_ENDPOINT, SAVE_SAVEAT, SAVE_EVERYSTEP = 0, 1, 2
 LAYOUT_TRAJ_MAJOR, LAYOUT_SOA = 0, 1
-RET_DEFAULT, RET_DTMIN, RET_MAXITERS = 0, 1, 2
+RET_DEFAULT, RET_DTMIN, RET_MAXITERS, RET_OUTPUT_FULL = 0, 1, 2, 3
 COMPAT_FIX_VERN9_INTERP = 1
 COMPAT_STRICT_CONTROLLER = 2
 
@@ -32,7 +32,7 @@ class SdeOptions(ctypes.Structure):
                 ("n_traj", ctypes.c_int64), ("t0", ctypes.c_double), ("tf", ctypes.c_double),
                 ("dt", ctypes.c_double), ("abstol", ctypes.c_double), ("reltol", ctypes.c_double),
                 ("n_steps", ctypes.c_int64), ("tgrid", ctypes.c_void_p), ("saveat", ctypes.c_void_p),
-                ("n_save", ctypes.c_int64), ("max_attempts", ctypes.c_int64)]
+                ("n_save", ctypes.c_int64), ("max_attempts", ctypes.c_int64), ("out_capacity", ctypes.c_int64)]
 
 
 class SdeError(RuntimeError):

@@ -112,6 +112,10 @@ class GPUSimpleRK4(_Alg):
     """Classic fixed-step RK4; always saves every step (src/rk4/gpurk4.jl:50)."""
 
 
+class GPUSimpleEuler(_Alg):
+    """Forward Euler; always saves every step (src/euler/gpueuler.jl:50)."""
+
+
 class GPUSimpleVern7(_Alg):
     """Fixed-step Verner 7(6) (src/verner/gpuvern7.jl:52)."""
 
@@ -224,9 +228,10 @@ class EnsembleSolution:
         return (ODESolution(self, i) for i in range(self.n_traj))
 
     def _series(self, i):
-        if self.layout == _lib.LAYOUT_TRAJ_MAJOR:
-            return self.u_raw[i]
-        return self.u_raw[:, :, i]
+        u = self.u_raw[i] if self.layout == _lib.LAYOUT_TRAJ_MAJOR else self.u_raw[:, :, i]
+        if self.t_series is not None:      # adaptive save_everystep: naccept + 1 states were saved
+            u = u[:min(int(self.naccept[i]) + 1, u.shape[0])]
+        return u
 
     def _u_of(self, i):
         if self.save_mode == _lib.SAVE_ENDPOINT:
@@ -236,6 +241,9 @@ class EnsembleSolution:
     def _t_of(self, i):
         if self.save_mode == _lib.SAVE_ENDPOINT and self.t_final is not None:
             return np.array([self.t0, self.t_final[i]], dtype=self.dtype)
+        if self.t_series is not None:
+            t = self.t_series[i] if self.layout == _lib.LAYOUT_TRAJ_MAJOR else self.t_series[:, i]
+            return t[:min(int(self.naccept[i]) + 1, t.shape[0])]
         return self.t_shared
 
 
@@ -247,7 +255,7 @@ def _as_T(x, dtype):
 
 
 def make_options(alg, dtype, n_traj, tspan, dt, abstol, reltol, saveat, save_mode, layout, compat,
-                 max_attempts, keep):
+                 max_attempts, keep, out_capacity=0):
     """Fill an SdeOptions.  `keep` collects the numpy arrays the struct points into."""
     o = _lib.SdeOptions()
     o.alg = alg.alg_id
@@ -258,6 +266,7 @@ def make_options(alg, dtype, n_traj, tspan, dt, abstol, reltol, saveat, save_mod
     o.dt = _as_T(dt, dtype)
     o.abstol, o.reltol = _as_T(abstol, dtype), _as_T(reltol, dtype)
     o.max_attempts = max_attempts
+    o.out_capacity = out_capacity
     if not alg.adaptive:
         grid = JuliaRange(o.t0, o.dt, o.tf, dtype).collect()   # _ts = tspan[1]:dt:tspan[2]
         if len(grid) == 0:
@@ -274,8 +283,8 @@ def make_options(alg, dtype, n_traj, tspan, dt, abstol, reltol, saveat, save_mod
 
 
 def _save_mode(alg, saveat, save_everystep):
-    if isinstance(alg, GPUSimpleRK4):
-        return _lib.SAVE_EVERYSTEP       # the reference's RK4 swallows saveat / save_everystep
+    if isinstance(alg, (GPUSimpleRK4, GPUSimpleEuler)):
+        return _lib.SAVE_EVERYSTEP       # the reference's RK4 / Euler swallow saveat / save_everystep
     if saveat is not None:
         return _lib.SAVE_SAVEAT
     return _lib.SAVE_EVERYSTEP if save_everystep else _lib.SAVE_ENDPOINT
@@ -311,8 +320,8 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
 
     # reference defaults (Float32 literals, converted to eltype(u0) where they meet the state)
     if dt is None:
-        if isinstance(alg, GPUSimpleRK4):
-            raise ValueError("dt is required for this algorithm")   # src/rk4/gpurk4.jl:56
+        if isinstance(alg, (GPUSimpleRK4, GPUSimpleEuler)):
+            raise ValueError("dt is required for this algorithm")   # src/rk4/gpurk4.jl:56, src/euler/gpueuler.jl:56
         dt = np.float32(0.1)
     abstol = np.float32(1e-6) if abstol is None else abstol
     reltol = np.float32(1e-3) if reltol is None else reltol
@@ -337,18 +346,24 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
             p_soa[:, i] = pi.p
 
     save_mode = _save_mode(alg, saveat, save_everystep)
-    if alg.adaptive and save_mode == _lib.SAVE_EVERYSTEP:
-        raise NotImplementedError(
-            "adaptive save_everystep=true (variable-length output) is not provided yet; "
-            "pass saveat=... or save_everystep=False")
     lay = _lib.LAYOUT_TRAJ_MAJOR if layout == "traj_major" else _lib.LAYOUT_SOA
+    capacity = 0
+    if alg.adaptive and save_mode == _lib.SAVE_EVERYSTEP:
+        # variable-length output (the reference push!es every accepted step, gpuatsit5.jl:301-303):
+        # the step sequence is deterministic, so a cheap endpoint-only pass gives the exact sizes
+        first = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, dt=dt, abstol=abstol, reltol=reltol,
+                             save_mode=_lib.SAVE_ENDPOINT, compat=compat, maxiters=maxiters, devices=devices)
+        if np.any(first["retcode"] == _lib.RET_DTMIN):
+            raise RuntimeError("dt<dtmin")
+        capacity = int(first["naccept"].max()) + 1
     raw = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, dt=dt, abstol=abstol, reltol=reltol,
                        saveat=saveat, save_mode=save_mode, layout=lay, compat=compat,
-                       maxiters=maxiters, devices=devices)
+                       maxiters=maxiters, devices=devices, out_capacity=capacity)
     if np.any(raw["retcode"] == _lib.RET_DTMIN):
         raise RuntimeError("dt<dtmin")       # the reference throws (src/tsit5/gpuatsit5.jl:256)
     sol = EnsembleSolution(n_traj=n, dtype=dtype, save_mode=save_mode, layout=lay, u0_soa=u0_soa,
                            u_raw=raw["u"], t_shared=raw["t_shared"], t_final=raw["t_final"],
+                           t_series=raw["t_series"],
                            t0=_as_T(base.tspan[0], dtype), naccept=raw["naccept"],
                            nreject=raw["nreject"], retcode=raw["retcode"], prob=ens, alg=alg)
     return sol[0] if single else sol
@@ -356,21 +371,26 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
 
 def solve_arrays(system, alg, u0_soa, p_soa, tspan, *, dt, abstol=1e-6, reltol=1e-3, saveat=None,
                  save_mode=_lib.SAVE_ENDPOINT, layout=_lib.LAYOUT_TRAJ_MAJOR, compat=0, maxiters=0,
-                 devices=None):
-    """Array-level entry: SoA host arrays in, raw arrays out, ONE sde_solve call (H2D, kernel(s), D2H)."""
+                 devices=None, out_capacity=0):
+    """Array-level entry: SoA host arrays in, raw arrays out, ONE sde_solve call (H2D, kernel(s), D2H).
+    Adaptive SAVE_EVERYSTEP needs out_capacity (slots per trajectory)."""
     dtype = u0_soa.dtype
     n = u0_soa.shape[1]
     keep = []
     o = make_options(alg, dtype, n, tspan, dt, abstol, reltol, saveat, save_mode, layout, compat,
-                     maxiters, keep)
+                     maxiters, keep, out_capacity)
     N = system.n_state
+    t_series = None
     if save_mode == _lib.SAVE_ENDPOINT:
         out_u = np.empty((N, n), dtype=dtype)
     else:
-        slots = int(o.n_save) if save_mode == _lib.SAVE_SAVEAT else int(o.n_steps) + 1
+        slots = (int(o.n_save) if save_mode == _lib.SAVE_SAVEAT
+                 else int(out_capacity) if alg.adaptive else int(o.n_steps) + 1)
         shape = (n, slots, N) if layout == _lib.LAYOUT_TRAJ_MAJOR else (slots, N, n)
         out_u = np.empty(shape, dtype=dtype)
-    t_final = np.empty(n, dtype=dtype) if alg.adaptive else None
+        if alg.adaptive and save_mode == _lib.SAVE_EVERYSTEP:
+            t_series = np.empty((n, slots) if layout == _lib.LAYOUT_TRAJ_MAJOR else (slots, n), dtype=dtype)
+    t_final = np.empty(n, dtype=dtype) if (alg.adaptive and t_series is None) else None
     nacc = np.zeros(n, dtype=np.int32)
     nrej = np.zeros(n, dtype=np.int32)
     ret = np.zeros(n, dtype=np.int32)
@@ -381,7 +401,8 @@ def solve_arrays(system, alg, u0_soa, p_soa, tspan, *, dt, abstol=1e-6, reltol=1
         dev = (ctypes.c_int * len(devices))(*devices)
         ndev = len(devices)
     rc = _lib.lib().sde_solve(system._handle, ctypes.byref(o), u0c.ctypes.data, pc.ctypes.data if pc.size else None,
-                              out_u.ctypes.data, t_final.ctypes.data if t_final is not None else None,
+                              out_u.ctypes.data,
+                              t_series.ctypes.data if t_series is not None else (t_final.ctypes.data if t_final is not None else None),
                               nacc.ctypes.data, nrej.ctypes.data, ret.ctypes.data, dev, ndev)
     _lib.check(rc)
     if alg.adaptive:
@@ -389,8 +410,8 @@ def solve_arrays(system, alg, u0_soa, p_soa, tspan, *, dt, abstol=1e-6, reltol=1
     else:
         t_shared = fixed_times(o, dtype)
         nacc[:] = o.n_steps
-    return dict(u=out_u, t_shared=t_shared, t_final=t_final, naccept=nacc, nreject=nrej, retcode=ret,
-                n_steps=int(o.n_steps))
+    return dict(u=out_u, t_shared=t_shared, t_final=t_final, t_series=t_series, naccept=nacc, nreject=nrej,
+                retcode=ret, n_steps=int(o.n_steps))
 
 
 def solve_device(system, alg, d_u0, d_p, tspan, *, dt, abstol=1e-6, reltol=1e-3, saveat=None,

@@ -58,7 +58,32 @@ struct RK4Method {
   template <bool> __device__ __forceinline__ void dense(T, T, const T*, T*) const {}
 };
 
+// ------------------------------------------------------------------------------------------
+// forward Euler (src/euler/gpueuler.jl:71-77): t = ts[i] (end of the step, like RK4's quirk Q1),
+// u = muladd(dt, k1, uprev).
+// ------------------------------------------------------------------------------------------
+template <class Sys, class T>
+struct EulerMethod {
+  static constexpr int N = Sys::N;
+  static constexpr bool kFSAL = false;
+  static constexpr bool kHasExtra = false;
+  static constexpr int kNB = 1;
+  __device__ __forceinline__ void seed(const T*, const T*, T) {}
+  __device__ __forceinline__ void begin_step() {}
+  template <bool>
+  __device__ __forceinline__ void stages(const T* uprev, T* u, const T* p, T t, T dt) {
+    T k1[N];
+    Sys::rhs(k1, uprev, p, t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = fma(dt, k1[i], uprev[i]);
+  }
+  template <bool> __device__ __forceinline__ void dense_prepare(const T*, const T*, T, T) {}
+  template <bool> __device__ __forceinline__ void dense_combine(const T*, T, const T*, T*) const {}
+  template <bool> __device__ __forceinline__ void dense(T, T, const T*, T*) const {}
+};
+
 template <class M> struct MethodTraits { static constexpr bool kTimeIsStepEnd = false; };
+template <class Sys, class T> struct MethodTraits<EulerMethod<Sys, T>> { static constexpr bool kTimeIsStepEnd = true; };
 template <class Sys, class T> struct MethodTraits<RK4Method<Sys, T>> { static constexpr bool kTimeIsStepEnd = true; };
 
 // ------------------------------------------------------------------------------------------
@@ -74,6 +99,13 @@ __device__ __forceinline__ void put_series(const KArgs<T>& a, i64 traj, i64 slot
 #pragma unroll
     for (int c = 0; c < N; ++c) a.out_u[(slot * N + c) * a.ld_out + traj] = v[c];
   }
+}
+
+template <class T>
+__device__ __forceinline__ void put_series_time(const KArgs<T>& a, i64 traj, i64 slot, T t) {
+  if (!a.out_t) return;
+  if (a.layout == kLayoutTrajMajor) a.out_t[traj * a.n_out + slot] = t;
+  else a.out_t[slot * a.ld_out + traj] = t;
 }
 
 template <class T, int N>
@@ -273,7 +305,14 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   Method m;
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
   T t = a.t0, dt = a.dt, told = a.t0, dtold = a.dt, qold = qoldinit;
-  double lqold = CtrlLog2<T>::beta2 * CtrlLog2<T>::qoldinit;   // beta2 * log2(qold)
+  __shared__ __align__(16) double s_ctrl[kC_count];
+  __shared__ __align__(16) T s_bt[Method::kNBT];
+  for (int i = threadIdx.x; i < kC_count; i += blockDim.x) s_ctrl[i] = k_ctrl[i];
+  if (threadIdx.x == 0) Method::load_btilde(s_bt);
+  __syncthreads();
+  const CtrlTab zlane = s_ctrl;
+  const double lqold0 = ctrl_const(zlane, CtrlLog2<T>::kBase + kL_beta2) * ctrl_const(zlane, CtrlLog2<T>::kBase + kL_qoldinit);
+  double lqold = lqold0;   // beta2 * log2(qold)
   int cur = 0, nacc = 0, nrej = 0;
   i64 traj = -1, attempts = 0;
   bool active = false, drained = false, newstep = false;
@@ -291,7 +330,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         if (traj < a.n_traj) {
           load_problem<T, N, NP>(a, traj, u, p);
           t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
-          lqold = CtrlLog2<T>::beta2 * CtrlLog2<T>::qoldinit;
+          lqold = lqold0;
           cur = 0; nacc = 0; nrej = 0; attempts = 0;
           m.seed(u, p, t);
           if (SAVE == kSaveAt) {
@@ -300,11 +339,15 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
               cur = 1;
             }
           }
+          if (SAVE == kSaveEveryStep) {   // us = [u0], ts = [t0]   (gpuatsit5.jl:220-224)
+            put_series<T, N>(a, traj, 0, u);
+            put_series_time<T>(a, traj, 0, t);
+          }
           active = true;
           newstep = true;
           if (!(t < tf)) {   // `while t < tspan[2]` never entered
             if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
-            if (a.out_t) a.out_t[traj] = t;
+            if (SAVE != kSaveEveryStep && a.out_t) a.out_t[traj] = t;
             if (a.naccept) a.naccept[traj] = 0;
             if (a.nreject) a.nreject[traj] = 0;
             if (a.retcode) a.retcode[traj] = kRetDefault;
@@ -336,7 +379,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         ++attempts;
         m.template stages<true>(uprev, u, p, t, dt);
         T e[N];
-        m.error(dt, e);
+        m.error(dt, e, s_bt);
         bool accept;
         if (kStrict) {
           // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
@@ -365,7 +408,8 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           }
         } else {
           // same formulas in the log2 domain (see sde_common.cuh); lqold = beta2 * log2(qold)
-          using L = CtrlLog2<T>;
+          constexpr int LB = CtrlLog2<T>::kBase;
+          const double one = ctrl_const(zlane, kC_one);
           double lE;        // log2(EEst)
           bool zero;        // iszero(EEst)
           if (sizeof(T) == 8) {
@@ -374,13 +418,13 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
 #pragma unroll
             for (int c = 0; c < N; ++c) {
               const double sc = (double)(a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
-              const double x = (double)e[c] * sde_rcp_fast(sc);
+              const double x = (double)e[c] * sde_rcp_fast(sc, one);
               ss = (c == 0) ? x * x : ss + x * x;
             }
             ss = ss * (1.0 / (double)N);
-            accept = !(ss > 1.0);
+            accept = !(ss > one);
             zero = (ss == 0.0);
-            lE = (ss != ss) ? ss : 0.5 * sde_log2_fast(ss);
+            lE = (ss != ss) ? ss : ctrl_const(zlane, kC_half) * sde_log2_fast(ss, zlane);
           } else {
             // FP32 state: EEst exactly as the reference (IEEE float div / sqrt), controller in FP64
             T EEst;
@@ -397,19 +441,26 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
             }
             accept = !(EEst > T(1));
             zero = (EEst == T(0));
-            lE = (EEst != EEst) ? (double)EEst : sde_log2_fast((double)EEst);
+            lE = (EEst != EEst) ? (double)EEst : sde_log2_fast((double)EEst, zlane);
           }
-          const double l11 = L::beta1 * lE;                       // log2(EEst^beta1)
-          if (!accept) {
-            const double ld = jl_min(L::inv_qmin, l11 - L::gamma);   // min(inv(qmin), q11/gamma)
-            dt = (T)((double)dt * sde_exp2_fast(-ld));
-          } else {
-            double lq = zero ? L::inv_qmax : l11 - lqold;         // q11 / qold^beta2
-            lq = max_fast(L::inv_qmax, min_fast(L::inv_qmin, lq - L::gamma));
-            lqold = L::beta2 * jl_max(lE, L::qoldinit);           // qold = max(EEst, qoldinit)
+          // reject:  dt /= min(inv(qmin), q11/gamma)                     -> exponent -min(l_invqmin, l11 - l_gamma)
+          // accept:  q = max(inv(qmax), min(inv(qmin), q11/qold^beta2/gamma)); dt /= q   -> exponent -lq
+          // (EEst > 1 on the reject path, so its min needs no NaN rule; the accept clamp uses the
+          //  FastMath forms, which map a NaN estimate to inv(qmax) like the reference)
+          const double l11 = ctrl_const(zlane, LB + kL_beta1) * lE;
+          const double lg = ctrl_const(zlane, LB + kL_gamma);
+          const double lmin = ctrl_const(zlane, LB + kL_inv_qmin);
+          const double lmax = ctrl_const(zlane, LB + kL_inv_qmax);
+          double lx = accept ? (zero ? lmax : l11 - lqold) : l11;
+          lx = lx - lg;
+          lx = min_fast(lmin, lx);
+          if (accept) {
+            lx = max_fast(lmax, lx);
+            const double lq0 = ctrl_const(zlane, LB + kL_qoldinit);
+            lqold = ctrl_const(zlane, LB + kL_beta2) * ((lE > lq0) ? lE : lq0);   // qold = max(EEst, qoldinit)
             dtold = dt;
-            dt = (T)((double)dt * sde_exp2_fast(-lq));
           }
+          dt = (T)((double)dt * sde_exp2_fast(-lx, zlane));
         }
         if (!accept) {
           ++nrej;
@@ -420,6 +471,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           else t = t + dtold;
           ++nacc;
           newstep = true;
+          if (SAVE == kSaveEveryStep) {   // push!(us, u); push!(ts, t)   (gpuatsit5.jl:301-303)
+            if ((i64)nacc < a.n_out) {
+              put_series<T, N>(a, traj, nacc, u);
+              put_series_time<T>(a, traj, nacc, t);
+            }
+          }
           if (SAVE == kSaveAt) {
             bool prepared = false;
             while (cur < a.n_save && a.saveat[cur] <= t) {
@@ -446,7 +503,18 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
           for (; cur < a.n_save; ++cur) put_series<T, N>(a, traj, cur, nanv);
         }
-        if (a.out_t) a.out_t[traj] = t;
+        if (SAVE == kSaveEveryStep) {
+          if (ret == kRetDefault && (i64)nacc >= a.n_out) ret = kRetOutputFull;
+          T nanv[N];
+#pragma unroll
+          for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
+          for (i64 s = (i64)nacc + 1; s < a.n_out; ++s) {   // unused capacity
+            put_series<T, N>(a, traj, s, nanv);
+            put_series_time<T>(a, traj, s, nanv[0]);
+          }
+        } else if (a.out_t) {
+          a.out_t[traj] = t;
+        }
         if (a.naccept) a.naccept[traj] = nacc;
         if (a.nreject) a.nreject[traj] = nrej;
         if (a.retcode) a.retcode[traj] = ret;

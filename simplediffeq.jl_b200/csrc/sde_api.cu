@@ -25,12 +25,12 @@
 static_assert((int)sde::kTsit5 == SDE_ALG_TSIT5 && (int)sde::kATsit5 == SDE_ALG_ATSIT5 &&
               (int)sde::kRK4 == SDE_ALG_RK4 && (int)sde::kVern7 == SDE_ALG_VERN7 &&
               (int)sde::kAVern7 == SDE_ALG_AVERN7 && (int)sde::kVern9 == SDE_ALG_VERN9 &&
-              (int)sde::kAVern9 == SDE_ALG_AVERN9, "alg ids");
+              (int)sde::kAVern9 == SDE_ALG_AVERN9 && (int)sde::kEuler == SDE_ALG_EULER, "alg ids");
 static_assert((int)sde::kSaveEndpoint == SDE_SAVE_ENDPOINT && (int)sde::kSaveAt == SDE_SAVE_SAVEAT &&
               (int)sde::kSaveEveryStep == SDE_SAVE_EVERYSTEP, "save ids");
 static_assert((int)sde::kLayoutTrajMajor == SDE_LAYOUT_TRAJ_MAJOR && (int)sde::kLayoutSoA == SDE_LAYOUT_SOA, "layout ids");
 static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin == SDE_RET_DTMIN &&
-              (int)sde::kRetMaxIters == SDE_RET_MAXITERS, "retcodes");
+              (int)sde::kRetMaxIters == SDE_RET_MAXITERS && (int)sde::kRetOutputFull == SDE_RET_OUTPUT_FULL, "retcodes");
 static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP &&
               (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER, "compat flags");
 
@@ -71,6 +71,11 @@ bool want_q2(const sde_options_t* o) {
 bool want_strict(const sde_options_t* o) { return is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER); }
 bool want_staged(const sde_options_t* o) {
   return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
+}
+int64_t out_slots(const sde_options_t* o) {
+  if (o->save_mode == SDE_SAVE_SAVEAT) return o->n_save;
+  if (o->save_mode == SDE_SAVE_EVERYSTEP) return is_adaptive(o->alg) ? o->out_capacity : o->n_steps + 1;
+  return 1;
 }
 // dynamic shared memory of the staged writer: must mirror sde::StageCfg
 // Tuning knob (NVRTC systems only, development): SDE_TUNE_STAGE_ELEMS=<elements staged per lane>
@@ -137,7 +142,7 @@ void init_builtins() {
 
 int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (!sys || !o) return fail(SDE_ERR_INVALID, "null system or options");
-  if (o->alg < 0 || o->alg > 6) return fail(SDE_ERR_INVALID, "unknown algorithm id %d", o->alg);
+  if (o->alg < 0 || o->alg > 7) return fail(SDE_ERR_INVALID, "unknown algorithm id %d", o->alg);
   if (o->dtype != SDE_F64 && o->dtype != SDE_F32) return fail(SDE_ERR_INVALID, "unknown dtype %d", o->dtype);
   if (o->save_mode < 0 || o->save_mode > 2) return fail(SDE_ERR_INVALID, "unknown save_mode %d", o->save_mode);
   if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
@@ -146,12 +151,12 @@ int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (o->save_mode == SDE_SAVE_SAVEAT) {
     if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(SDE_ERR_INVALID, "saveat array missing");
     if (o->n_save > 0x7fffffff) return fail(SDE_ERR_INVALID, "n_save too large");
-    if (o->alg == SDE_ALG_RK4)
-      return fail(SDE_ERR_UNSUPPORTED, "GPUSimpleRK4 has no saveat (the reference ignores the keyword and saves every step)");
+    if (o->alg == SDE_ALG_RK4 || o->alg == SDE_ALG_EULER)
+      return fail(SDE_ERR_UNSUPPORTED, "GPUSimpleRK4 / GPUSimpleEuler have no saveat (the reference ignores the keyword and saves every step)");
   }
   if (is_adaptive(o->alg)) {
-    if (o->save_mode == SDE_SAVE_EVERYSTEP)
-      return fail(SDE_ERR_UNSUPPORTED, "save_everystep=true (variable-length output) is not provided for adaptive algorithms yet");
+    if (o->save_mode == SDE_SAVE_EVERYSTEP && o->out_capacity < 1)
+      return fail(SDE_ERR_INVALID, "adaptive SDE_SAVE_EVERYSTEP needs out_capacity >= 1 (slots per trajectory)");
   } else {
     if (o->n_steps < 0) return fail(SDE_ERR_INVALID, "n_steps < 0");
   }
@@ -165,6 +170,7 @@ const char* method_name(int alg) {
   switch (alg) {
     case SDE_ALG_TSIT5: case SDE_ALG_ATSIT5: return "sde::Tsit5Method";
     case SDE_ALG_RK4: return "sde::RK4Method";
+    case SDE_ALG_EULER: return "sde::EulerMethod";
     case SDE_ALG_VERN7: case SDE_ALG_AVERN7: return "sde::Vern7Method";
     default: return "sde::Vern9Method";
   }
@@ -344,8 +350,7 @@ int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const vo
   a.max_attempts = o->max_attempts;
   a.out_u = (T*)d_out_u;
   a.ld_out = ld_out;
-  a.n_out = o->save_mode == SDE_SAVE_SAVEAT ? o->n_save
-            : o->save_mode == SDE_SAVE_EVERYSTEP ? o->n_steps + 1 : 1;
+  a.n_out = out_slots(o);
   a.out_t = adaptive ? (T*)d_out_t : nullptr;
   a.naccept = d_nacc; a.nreject = d_nrej; a.retcode = d_ret;
 
@@ -430,10 +435,6 @@ int launch(sde_system_s* sys, const sde_options_t* o, const void* d_u0, const vo
   return launch_t<float>(sys, o, fn, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
 }
 
-int64_t out_slots(const sde_options_t* o) {
-  return o->save_mode == SDE_SAVE_SAVEAT ? o->n_save
-         : o->save_mode == SDE_SAVE_EVERYSTEP ? o->n_steps + 1 : 1;
-}
 
 // --------------------------------------------------------------------------------------------
 // one device shard of a host-buffer solve: trajectories [lo, hi) in chunks that fit the budget
@@ -451,7 +452,7 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t l
     // device memory budget per chunk: keep well below HBM capacity
     size_t free_b = 0, total_b = 0;
     SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_traj = es * ((size_t)N + NP + (size_t)N * slots + 1) + 12;
+    const size_t per_traj = es * ((size_t)N + NP + (size_t)(N + 1) * slots + 1) + 12;
     int64_t chunk = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
     chunk = std::min<int64_t>(chunk, hi - lo);
     if (chunk > 32) chunk -= chunk % 32;
@@ -470,7 +471,8 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t l
       SDE_TRY(cudaMalloc((void**)&d_u0, es * N * chunk));
       if (NP) SDE_TRY(cudaMalloc((void**)&d_p, es * NP * chunk));
       SDE_TRY(cudaMalloc((void**)&d_out, es * N * slots * chunk));
-      if (adaptive && out_t) SDE_TRY(cudaMalloc((void**)&d_t, es * chunk));
+      const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
+      if (adaptive && out_t) SDE_TRY(cudaMalloc((void**)&d_t, es * chunk * (t_series ? slots : 1)));
       if (nacc) SDE_TRY(cudaMalloc((void**)&d_na, 4 * chunk));
       if (nrej) SDE_TRY(cudaMalloc((void**)&d_nr, 4 * chunk));
       if (ret) SDE_TRY(cudaMalloc((void**)&d_rc, 4 * chunk));
@@ -492,7 +494,14 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t l
       } else {
         SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, d_out, es * chunk, es * n, (size_t)N * slots, cudaMemcpyDeviceToHost, st));
       }
-      if (d_t) SDE_TRY(cudaMemcpyAsync(out_t + es * c0, d_t, es * n, cudaMemcpyDeviceToHost, st));
+      if (d_t) {
+        const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
+        if (!t_series) SDE_TRY(cudaMemcpyAsync(out_t + es * c0, d_t, es * n, cudaMemcpyDeviceToHost, st));
+        else if (o->layout == SDE_LAYOUT_TRAJ_MAJOR)
+          SDE_TRY(cudaMemcpyAsync(out_t + es * slots * c0, d_t, es * slots * n, cudaMemcpyDeviceToHost, st));
+        else
+          SDE_TRY(cudaMemcpy2DAsync(out_t + es * c0, es * n_all, d_t, es * chunk, es * n, (size_t)slots, cudaMemcpyDeviceToHost, st));
+      }
       if (d_na) SDE_TRY(cudaMemcpyAsync(nacc + c0, d_na, 4 * n, cudaMemcpyDeviceToHost, st));
       if (d_nr) SDE_TRY(cudaMemcpyAsync(nrej + c0, d_nr, 4 * n, cudaMemcpyDeviceToHost, st));
       if (d_rc) SDE_TRY(cudaMemcpyAsync(ret + c0, d_rc, 4 * n, cudaMemcpyDeviceToHost, st));
@@ -644,8 +653,8 @@ int sde_fixed_times(const sde_options_t* o, void* out, int64_t n, int64_t* n_wri
     const T dt = (T)o->dt;
     if (o->save_mode == SDE_SAVE_SAVEAT) {
       memcpy(t, o->saveat, sizeof(T) * o->n_save);
-    } else if (o->alg == SDE_ALG_RK4) {
-      // ts = tspan[1]:dt:tspan[2] itself (src/rk4/gpurk4.jl:65)
+    } else if (o->alg == SDE_ALG_RK4 || o->alg == SDE_ALG_EULER) {
+      // ts = tspan[1]:dt:tspan[2] itself (src/rk4/gpurk4.jl:65, src/euler/gpueuler.jl:66)
       if (o->save_mode == SDE_SAVE_EVERYSTEP) for (int64_t k = 0; k <= o->n_steps; ++k) t[k] = grid(k);
       else { t[0] = (T)o->t0; t[1] = grid(o->n_steps); }
     } else {

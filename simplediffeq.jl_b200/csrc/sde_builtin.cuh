@@ -34,6 +34,7 @@ template <class Sys, class T>
 inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool staged) {
   using TS = Tsit5Method<Sys, T>;
   using RK = RK4Method<Sys, T>;
+  using EU = EulerMethod<Sys, T>;
   using V7 = Vern7Method<Sys, T>;
   using V9 = Vern9Method<Sys, T>;
 #define SDE_FIXED(M, S, Q) pick_fixed<Sys, T, M, S, Q>(staged)
@@ -50,6 +51,10 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool 
       if (save == kSaveEndpoint) return SDE_FIXED(RK, kSaveEndpoint, false);
       if (save == kSaveEveryStep) return SDE_FIXED(RK, kSaveEveryStep, false);
       break;
+    case kEuler:  // like RK4: no saveat in the reference
+      if (save == kSaveEndpoint) return SDE_FIXED(EU, kSaveEndpoint, false);
+      if (save == kSaveEveryStep) return SDE_FIXED(EU, kSaveEveryStep, false);
+      break;
     case kVern7:
       if (save == kSaveEndpoint) return SDE_FIXED(V7, kSaveEndpoint, false);
       if (save == kSaveAt) return SDE_FIXED(V7, kSaveAt, false);
@@ -63,14 +68,17 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool 
     case kATsit5:
       if (save == kSaveEndpoint) return SDE_ADAPT(TS, kSaveEndpoint, false);
       if (save == kSaveAt) return SDE_ADAPT(TS, kSaveAt, false);
+      if (save == kSaveEveryStep) return SDE_ADAPT(TS, kSaveEveryStep, false);
       break;
     case kAVern7:
       if (save == kSaveEndpoint) return SDE_ADAPT(V7, kSaveEndpoint, false);
       if (save == kSaveAt) return SDE_ADAPT(V7, kSaveAt, false);
+      if (save == kSaveEveryStep) return SDE_ADAPT(V7, kSaveEveryStep, false);
       break;
     case kAVern9:
       if (save == kSaveEndpoint) return SDE_ADAPT(V9, kSaveEndpoint, true);
       if (save == kSaveAt) return SDE_ADAPT(V9, kSaveAt, true);
+      if (save == kSaveEveryStep) return SDE_ADAPT(V9, kSaveEveryStep, true);
       break;
   }
 #undef SDE_FIXED

@@ -3,7 +3,7 @@ import numpy as np
 
 ALG_NAMES = {"GPUSimpleTsit5": "Tsit5", "GPUSimpleATsit5": "ATsit5", "GPUSimpleRK4": "RK4",
              "GPUSimpleVern7": "Vern7", "GPUSimpleAVern7": "AVern7", "GPUSimpleVern9": "Vern9",
-             "GPUSimpleAVern9": "AVern9"}
+             "GPUSimpleAVern9": "AVern9", "GPUSimpleEuler": "Euler"}
 
 
 def lorenz_sweep(n, dtype=np.float64, rho_max=21.0):

@@ -23,7 +23,7 @@ from simplediffeq_b200 import jl_range  # noqa: E402
 
 CASES = []
 for dtype in ("float64", "float32"):
-    for alg in ("Tsit5", "RK4", "Vern7", "Vern9"):
+    for alg in ("Tsit5", "RK4", "Vern7", "Vern9", "Euler"):
         CASES.append(dict(system="lorenz", alg=alg, dtype=dtype, n=6, tspan=[0.0, 1.0], dt=0.01, mode="endpoint"))
         CASES.append(dict(system="nonautonomous", alg=alg, dtype=dtype, n=4, tspan=[0.0, 1.0], dt=0.05, mode="endpoint"))
     for alg in ("Tsit5", "Vern7", "Vern9"):

@@ -14,7 +14,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 
 # ids of oracle.cpp (deliberately NOT imported from the product's headers)
-ALG = dict(Tsit5=0, ATsit5=1, RK4=2, Vern7=3, AVern7=4, Vern9=5, AVern9=6)
+ALG = dict(Tsit5=0, ATsit5=1, RK4=2, Vern7=3, AVern7=4, Vern9=5, AVern9=6, Euler=7)
 SYS = dict(lorenz=0, vanderpol=1, robertson=2, nbody=3, lineardecay=4, scalargrowth=5,
            nonautonomous=6, user=100)
 SAVE_ENDPOINT, SAVE_SAVEAT, SAVE_EVERYSTEP = 0, 1, 2

@@ -85,11 +85,12 @@ def test_header_ids_match_python_ids(sde):
     assert ids["SDE_ALG_AVERN7"] == _lib.ALG_IDS["GPUSimpleAVern7"]
     assert ids["SDE_ALG_VERN9"] == _lib.ALG_IDS["GPUSimpleVern9"]
     assert ids["SDE_ALG_AVERN9"] == _lib.ALG_IDS["GPUSimpleAVern9"]
+    assert ids["SDE_ALG_EULER"] == _lib.ALG_IDS["GPUSimpleEuler"] == 7
     assert (ids["SDE_SAVE_ENDPOINT"], ids["SDE_SAVE_SAVEAT"], ids["SDE_SAVE_EVERYSTEP"]) == (0, 1, 2)
     assert (ids["SDE_LAYOUT_TRAJ_MAJOR"], ids["SDE_LAYOUT_SOA"]) == (_lib.LAYOUT_TRAJ_MAJOR, _lib.LAYOUT_SOA)
     assert ids["SDE_COMPAT_FIX_VERN9_INTERP"] == _lib.COMPAT_FIX_VERN9_INTERP
     assert ids["SDE_COMPAT_STRICT_CONTROLLER"] == _lib.COMPAT_STRICT_CONTROLLER
-    assert ctypes.sizeof(_lib.SdeOptions) == 6 * 4 + 8 + 5 * 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.SdeOptions) == 6 * 4 + 8 + 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8
 
 
 def test_builtin_registry(sde):
@@ -107,7 +108,7 @@ def test_every_builtin_kernel_exists(sde):
     from simplediffeq_b200 import _lib
     L = _lib.lib()
     algs = [sde.GPUSimpleTsit5(), sde.GPUSimpleATsit5(), sde.GPUSimpleRK4(), sde.GPUSimpleVern7(),
-            sde.GPUSimpleAVern7(), sde.GPUSimpleVern9(), sde.GPUSimpleAVern9()]
+            sde.GPUSimpleAVern7(), sde.GPUSimpleVern9(), sde.GPUSimpleAVern9(), sde.GPUSimpleEuler()]
     n_ok = 0
     for name in sde.systems.names():
         sysm = getattr(sde.systems, name)
@@ -116,12 +117,12 @@ def test_every_builtin_kernel_exists(sde):
                 for mode in (0, 1, 2):
                     keep = []
                     o = sde.api.make_options(alg, np.dtype(dtype), 4, (0.0, 1.0), 0.1, 1e-6, 1e-3,
-                                             np.array([0.5]) if mode == 1 else None, mode, 0, 0, 0, keep)
+                                             np.array([0.5]) if mode == 1 else None, mode, 0, 0, 0, keep, out_capacity=16)
                     rc = L.sde_system_prepare(sysm._handle, ctypes.byref(o))
-                    unsupported = (alg.adaptive and mode == 2) or (isinstance(alg, sde.GPUSimpleRK4) and mode == 1)
+                    unsupported = isinstance(alg, (sde.GPUSimpleRK4, sde.GPUSimpleEuler)) and mode == 1
                     assert (rc == -4) if unsupported else (rc == 0), (name, alg, dtype, mode, L.sde_last_error())
                     n_ok += rc == 0
-    assert n_ok == 7 * 2 * (3 + 2 + 3 + 3 + 2 + 2 + 2)
+    assert n_ok == 7 * 2 * (3 + 3 + 2 + 3 + 3 + 3 + 3 + 2)
 
 
 def test_option_validation_errors(sde):
@@ -251,8 +252,7 @@ def test_problem_types_and_defaults(sde):
     assert _save_mode(sde.GPUSimpleTsit5(), None, False) == 0
     assert _save_mode(sde.GPUSimpleTsit5(), [0.5], True) == 1
     assert _save_mode(sde.GPUSimpleRK4(), [0.5], False) == 2        # RK4 swallows both keywords
-    with pytest.raises(NotImplementedError):
-        sde.solve(prob, sde.GPUSimpleATsit5())                      # adaptive save_everystep=true: next round
+    assert _save_mode(sde.GPUSimpleATsit5(), None, True) == 2        # adaptive save_everystep=true: variable length
 
 
 def test_fixed_times_match_the_reference_rules(sde):

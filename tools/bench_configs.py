@@ -101,7 +101,7 @@ def main():
             gbs = n * 24072 / ms / 1e6
             emit(config="5: Lorenz 4M Tsit5 saveat=0:0.01:10 dt=%g %s" % (dt, nm), ms=ms, hbm_gbs=gbs, hbm_frac=gbs / HBM,
                  steps_per_s=n * r["n_steps"] / ms * 1e3, bytes_per_traj=24072)
-            del out
+            del out, r
             torch.cuda.empty_cache()
 
 

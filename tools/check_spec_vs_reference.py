@@ -70,6 +70,13 @@ def main():
             print("MISSING in gpurk4.jl:", s)
             ok = False
     print("%-28s literal statements: %s" % ("src/rk4/gpurk4.jl", "ok" if ok else "MISMATCH"))
+    # ---- Euler
+    src = stripped("src/euler/gpueuler.jl")
+    for s_ in ["t=ts[i]", "k1=f(u,p,t)", "u=uprev+dt*k1", "us[i]=u"]:
+        if s_ not in src:
+            print("MISSING in gpueuler.jl:", s_)
+            ok = False
+    print("%-28s literal statements: %s" % ("src/euler/gpueuler.jl", "ok" if ok else "MISMATCH"))
     # ---- Vern7
     sp = G.spec_vern7(v)
     exp = [sums(t) for _, _, t in sp["stages"] if len(t) > 1] + [sums(sp["update"]), sums(sp["err"])]

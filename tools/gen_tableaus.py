@@ -304,10 +304,17 @@ def emit_method(sp, refnote):
         o.append("    Sys::rhs(k7, u, p, t + dt);\n")
     o.append("  }\n")
     # ---- error
-    o.append("\n  // embedded error estimate: e = dt * (btilde . k)\n")
-    o.append("  __device__ __forceinline__ void error(T dt, T* e) const {\n")
+    o.append("\n  // embedded error estimate: e = dt * (btilde . k).  bt = the btilde coefficients in the order of\n"
+             "  // load_btilde(); the adaptive kernels keep them in shared memory (uniform-register relief).\n")
+    o.append("  static constexpr int kNBT = %d;\n" % len(sp["err"]))
+    o.append("  __device__ __forceinline__ static void load_btilde(T* bt) {\n")
     o.append("    const %sCoef<T>& C = Coefs<T>::%s();\n" % (name, low))
-    o.append("#pragma unroll\n    for (int i = 0; i < N; ++i)\n      e[i] = dt * (%s);\n  }\n" % fold(sp["err"]))
+    for idx, (n, j) in enumerate(sp["err"]):
+        o.append("    bt[%d] = C.%s;\n" % (idx, n))
+    o.append("  }\n")
+    o.append("  __device__ __forceinline__ void error(T dt, T* e, const T* bt) const {\n")
+    bt_terms = [("bt[%d]" % idx, j) for idx, (n, j) in enumerate(sp["err"])]
+    o.append("#pragma unroll\n    for (int i = 0; i < N; ++i)\n      e[i] = dt * (%s);\n  }\n" % fold(bt_terms, coef=lambda n: n))
     # ---- extra stages
     o.append("\n  // extra stages needed by the dense output (none for Tsit5). tx = time base the\n"
              "  // reference passes to f (quirk Q3), kQ2: reference-exact fixed-step Vern9 pairs the\n"
