@@ -314,11 +314,16 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   const double lqold0 = ctrl_const(zlane, CtrlLog2<T>::kBase + kL_beta2) * ctrl_const(zlane, CtrlLog2<T>::kBase + kL_qoldinit);
   double lqold = lqold0;   // beta2 * log2(qold)
   int cur = 0, nacc = 0, nrej = 0;
-  i64 traj = -1, attempts = 0;
-  bool active = false, drained = false, newstep = false;
+  i64 traj = -1;
+  bool active = false, drained = false;
+  // attempts are counted as nacc + nrej (int32, like the naccept / nreject outputs); 0 = the
+  // reference's "no maxiters" = the int32 range
+  const int attempt_limit = (a.max_attempts > 0 && a.max_attempts < (i64)0x7fffffff) ? (int)a.max_attempts : 0x7fffffff;
 
   for (;;) {
-    // ---- work queue: idle lanes fetch the next trajectory (one atomic per warp per refill)
+    // ---- work queue: idle lanes fetch the next trajectory (one atomic per warp per refill).
+    // Fast path while every lane is busy: one vote.
+    if (__any_sync(FULL, !active)) {
     const unsigned want = __ballot_sync(FULL, !active && !drained);
     if (want) {
       const int leader = __ffs(want) - 1;
@@ -331,8 +336,11 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           load_problem<T, N, NP>(a, traj, u, p);
           t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
           lqold = lqold0;
-          cur = 0; nacc = 0; nrej = 0; attempts = 0;
+          cur = 0; nacc = 0; nrej = 0;
           m.seed(u, p, t);
+#pragma unroll
+          for (int c = 0; c < N; ++c) uprev[c] = u[c];
+          m.begin_step();
           if (SAVE == kSaveAt) {
             if (a.n_save > 0 && a.t0 == a.saveat[0]) {
               put_series<T, N>(a, traj, 0, u);
@@ -344,7 +352,6 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
             put_series_time<T>(a, traj, 0, t);
           }
           active = true;
-          newstep = true;
           if (!(t < tf)) {   // `while t < tspan[2]` never entered
             if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
             if (SAVE != kSaveEveryStep && a.out_t) a.out_t[traj] = t;
@@ -362,21 +369,15 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
       if (__all_sync(FULL, drained)) break;   // warp-vote exit: nothing left anywhere
       continue;
     }
+    }
 
     if (active) {
-      if (newstep) {
-#pragma unroll
-        for (int c = 0; c < N; ++c) uprev[c] = u[c];
-        m.begin_step();
-        newstep = false;
-      }
       int ret = -1;
       if ((double)dt < thr) {
         ret = kRetDtMin;                               // error("dt<dtmin")
-      } else if (a.max_attempts != 0 && attempts >= a.max_attempts) {
+      } else if (nacc + nrej >= attempt_limit) {
         ret = kRetMaxIters;
       } else {
-        ++attempts;
         m.template stages<true>(uprev, u, p, t, dt);
         T e[N];
         m.error(dt, e, s_bt);
@@ -385,12 +386,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
           T EEst;
           if (N == 1) {
-            EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
+            EEst = sde_abs(e[0] / (a.abstol + max_abs_nan2(uprev[0], u[0]) * a.reltol));
           } else {
             T ssum = T(0);
 #pragma unroll
             for (int c = 0; c < N; ++c) {
-              const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+              const T sc = e[c] / (a.abstol + max_abs_nan2(uprev[c], u[c]) * a.reltol);
               ssum = (c == 0) ? sc * sc : ssum + sc * sc;
             }
             EEst = sde_sqrt(ssum / T(N));
@@ -410,37 +411,35 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           // same formulas in the log2 domain (see sde_common.cuh); lqold = beta2 * log2(qold)
           constexpr int LB = CtrlLog2<T>::kBase;
           const double one = ctrl_const(zlane, kC_one);
-          double lE;        // log2(EEst)
-          bool zero;        // iszero(EEst)
+          double lE;        // log2(EEst); an estimate of exactly zero gives about -1023 (f64: -511), which
+                            // the accept clamp turns into inv(qmax) like the reference's `EEst == 0` branch
           if (sizeof(T) == 8) {
             // EEst^2 = sum((e_i / sc_i)^2) / N with Newton reciprocals: no division, no sqrt
             double ss = 0.0;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
-              const double sc = (double)(a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+              const double sc = (double)(a.abstol + max_abs_nan2(uprev[c], u[c]) * a.reltol);
               const double x = (double)e[c] * sde_rcp_fast(sc, one);
               ss = (c == 0) ? x * x : ss + x * x;
             }
             ss = ss * (1.0 / (double)N);
             accept = !(ss > one);
-            zero = (ss == 0.0);
             lE = (ss != ss) ? ss : ctrl_const(zlane, kC_half) * sde_log2_fast(ss, zlane);
           } else {
             // FP32 state: EEst exactly as the reference (IEEE float div / sqrt), controller in FP64
             T EEst;
             if (N == 1) {
-              EEst = sde_abs(e[0] / (a.abstol + jl_max(sde_abs(uprev[0]), sde_abs(u[0])) * a.reltol));
+              EEst = sde_abs(e[0] / (a.abstol + max_abs_nan2(uprev[0], u[0]) * a.reltol));
             } else {
               T ssum = T(0);
 #pragma unroll
               for (int c = 0; c < N; ++c) {
-                const T sc = e[c] / (a.abstol + jl_max(sde_abs(uprev[c]), sde_abs(u[c])) * a.reltol);
+                const T sc = e[c] / (a.abstol + max_abs_nan2(uprev[c], u[c]) * a.reltol);
                 ssum = (c == 0) ? sc * sc : ssum + sc * sc;
               }
               EEst = sde_sqrt(ssum / T(N));
             }
             accept = !(EEst > T(1));
-            zero = (EEst == T(0));
             lE = (EEst != EEst) ? (double)EEst : sde_log2_fast((double)EEst, zlane);
           }
           // reject:  dt /= min(inv(qmin), q11/gamma)                     -> exponent -min(l_invqmin, l11 - l_gamma)
@@ -451,11 +450,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           const double lg = ctrl_const(zlane, LB + kL_gamma);
           const double lmin = ctrl_const(zlane, LB + kL_inv_qmin);
           const double lmax = ctrl_const(zlane, LB + kL_inv_qmax);
-          double lx = accept ? (zero ? lmax : l11 - lqold) : l11;
+          // (on the reject path l11 > 0 > lmax + lg, so the lower clamp is a no-op there and is applied
+          //  unconditionally)
+          double lx = accept ? l11 - lqold : l11;
           lx = lx - lg;
-          lx = min_fast(lmin, lx);
+          lx = max_fast(lmax, min_fast(lmin, lx));
           if (accept) {
-            lx = max_fast(lmax, lx);
             const double lq0 = ctrl_const(zlane, LB + kL_qoldinit);
             lqold = ctrl_const(zlane, LB + kL_beta2) * ((lE > lq0) ? lE : lq0);   // qold = max(EEst, qoldinit)
             dtold = dt;
@@ -465,12 +465,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         if (!accept) {
           ++nrej;
         } else {
-          dt = jl_min(sde_abs(dt), sde_abs(tf - t - dtold));
+          const T rem = tf - t - dtold;
+          dt = min_abs_nan1(dt, rem);        // min(abs(dt), abs(tf - t - dtold))
           told = t;
-          if ((double)(tf - t - dtold) < thr) t = tf;
+          if ((double)rem < thr) t = tf;
           else t = t + dtold;
           ++nacc;
-          newstep = true;
           if (SAVE == kSaveEveryStep) {   // push!(us, u); push!(ts, t)   (gpuatsit5.jl:301-303)
             if ((i64)nacc < a.n_out) {
               put_series<T, N>(a, traj, nacc, u);
@@ -493,6 +493,11 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
             }
           }
           if (!(t < tf)) ret = kRetDefault;
+          // the next step starts from the accepted state (after the dense output, which reads the
+          // old uprev / k1)
+#pragma unroll
+          for (int c = 0; c < N; ++c) uprev[c] = u[c];
+          m.begin_step();
         }
       }
       if (ret >= 0) {   // trajectory finished (or failed): publish and free the lane

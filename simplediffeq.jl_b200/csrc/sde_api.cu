@@ -437,9 +437,35 @@ int launch(sde_system_s* sys, const sde_options_t* o, const void* d_u0, const vo
 
 
 // --------------------------------------------------------------------------------------------
-// one device shard of a host-buffer solve: trajectories [lo, hi) in chunks that fit the budget
+// Source of contiguous trajectory ranges for one device of a host-buffer solve.
+//   static : the device owns [lo, hi) = [floor(gN/G), floor((g+1)N/G)) and walks it in pieces that
+//            fit its memory budget (fixed-step algorithms: every trajectory costs the same);
+//   dynamic: all devices pull pieces of `grain` trajectories from one shared counter (adaptive
+//            algorithms: step counts vary 10x along a parameter sweep, so equal index ranges are
+//            not equal work -- the host-level analogue of the kernels' work queue).
 // --------------------------------------------------------------------------------------------
-int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t lo, int64_t hi,
+struct RangeSource {
+  int64_t lo = 0, hi = 0;                    // static range (cursor = lo)
+  std::atomic<int64_t>* shared = nullptr;    // dynamic: next unassigned trajectory
+  int64_t total = 0, grain = 0;
+  bool next(int64_t max_len, int64_t* a, int64_t* b) {
+    if (shared) {
+      const int64_t len = std::min(max_len, grain);
+      const int64_t s = shared->fetch_add(len);
+      if (s >= total) return false;
+      *a = s; *b = std::min(total, s + len);
+      return true;
+    }
+    if (lo >= hi) return false;
+    *a = lo; *b = std::min(hi, lo + max_len);
+    lo = *b;
+    return true;
+  }
+  int64_t max_piece() const { return shared ? std::min(grain, total) : hi - lo; }
+};
+
+// one device of a host-buffer solve
+int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSource src,
                 const char* u0, const char* p, char* out_u, char* out_t, int32_t* nacc, int32_t* nrej,
                 int32_t* ret, std::string* err) {
   auto body = [&]() -> int {
@@ -454,7 +480,7 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t l
     SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t per_traj = es * ((size_t)N + NP + (size_t)(N + 1) * slots + 1) + 12;
     int64_t chunk = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
-    chunk = std::min<int64_t>(chunk, hi - lo);
+    chunk = std::min<int64_t>(chunk, src.max_piece());
     if (chunk > 32) chunk -= chunk % 32;
     cudaStream_t st;
     SDE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -477,8 +503,9 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, int64_t l
       if (nrej) SDE_TRY(cudaMalloc((void**)&d_nr, 4 * chunk));
       if (ret) SDE_TRY(cudaMalloc((void**)&d_rc, 4 * chunk));
     }
-    for (int64_t c0 = lo; c0 < hi; c0 += chunk) {
-      const int64_t n = std::min<int64_t>(chunk, hi - c0);
+    int64_t c0 = 0, c1 = 0;
+    while (chunk > 0 && src.next(chunk, &c0, &c1)) {
+      const int64_t n = c1 - c0;
       // H2D: SoA rows of the shard (host pitch = n_all elements, device pitch = chunk elements)
       SDE_TRY(cudaMemcpy2DAsync(d_u0, es * chunk, u0 + es * c0, es * n_all, es * n, N, cudaMemcpyHostToDevice, st));
       if (NP) SDE_TRY(cudaMemcpy2DAsync(d_p, es * chunk, p + es * c0, es * n_all, es * n, NP, cudaMemcpyHostToDevice, st));
@@ -619,17 +646,31 @@ int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const 
   if (n_dev < 0 || (n_dev > 0 && !devices)) return fail(SDE_ERR_INVALID, "bad device list");
   if (opt->n_traj == 0) return SDE_OK;
   if (n_dev <= 1) {
-    return solve_shard(sys, opt, n_dev == 1 ? devices[0] : -1, 0, opt->n_traj, (const char*)u0,
+    RangeSource all;
+    all.lo = 0; all.hi = opt->n_traj;
+    return solve_shard(sys, opt, n_dev == 1 ? devices[0] : -1, all, (const char*)u0,
                        (const char*)p, (char*)out_u, (char*)out_t, naccept, nreject, retcode, nullptr);
   }
   // contiguous index ranges [g*N/G, (g+1)*N/G), one host thread + stream per device, no collective
+  // (adaptive algorithms: pieces of `grain` trajectories from a shared counter instead, see RangeSource)
   std::vector<std::thread> th;
   std::vector<int> rcs(n_dev, SDE_OK);
   std::vector<std::string> errs(n_dev);
+  std::atomic<int64_t> cursor{0};
   for (int g = 0; g < n_dev; ++g) {
-    const int64_t lo = opt->n_traj * g / n_dev, hi = opt->n_traj * (g + 1) / n_dev;
+    RangeSource src;
+    if (is_adaptive(opt->alg) && !getenv("SDE_TUNE_STATIC_SHARDS")) {   // env knob: measurement only
+      src.shared = &cursor;
+      src.total = opt->n_traj;
+      int64_t grain = opt->n_traj / ((int64_t)n_dev * 8);          // ~8 pieces per device
+      grain = std::max<int64_t>(grain, 1 << 16);                     // but never tiny launches
+      src.grain = (grain + 31) & ~(int64_t)31;
+    } else {
+      src.lo = opt->n_traj * g / n_dev;
+      src.hi = opt->n_traj * (g + 1) / n_dev;
+    }
     th.emplace_back([=, &rcs, &errs]() {
-      rcs[g] = solve_shard(sys, opt, devices[g], lo, hi, (const char*)u0, (const char*)p, (char*)out_u,
+      rcs[g] = solve_shard(sys, opt, devices[g], src, (const char*)u0, (const char*)p, (char*)out_u,
                            (char*)out_t, naccept, nreject, retcode, &errs[g]);
     });
   }

@@ -1,0 +1,98 @@
+"""CPU checks of the step-size controller's device math (csrc/device/sde_common.cuh), compiled for the
+host through tests/ctrl_host_emul.cpp: the table-driven log2 / exp2 against mpmath, the generated table
+against its generator, and the shortened NaN-propagating min/max against Julia's Base.min/max on the
+domain their invariants allow."""
+import ctypes
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "libctrl_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-shared", "-fPIC",
+                           os.path.join(ROOT, "tests", "ctrl_host_emul.cpp"), "-o", out])
+    L = ctypes.CDLL(out)
+    for f in ("emul_max_abs_nan2", "emul_min_abs_nan1", "emul_jl_max", "emul_jl_min"):
+        getattr(L, f).restype = ctypes.c_double
+        getattr(L, f).argtypes = [ctypes.c_double, ctypes.c_double]
+    L.emul_ctrl.restype = ctypes.c_double
+    return L
+
+
+def _apply(fn, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    fn(x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(x)))
+    return out
+
+
+def test_generated_table_is_current():
+    """sde_ctrl_tables_gen.cuh is what tools/gen_ctrl_tables.py writes (no hand edits)."""
+    path = os.path.join(ROOT, "simplediffeq.jl_b200", "csrc", "device", "sde_ctrl_tables_gen.cuh")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_ctrl_tables.py")],
+                          stdout=subprocess.DEVNULL)
+    assert open(path).read() == before
+
+
+def test_log2_fast_accuracy(emul):
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(20261017)
+    # squared error norms seen by the controller: 1e-30 .. 1e10, dense around 1, exact powers of two
+    x = np.concatenate([10.0 ** rng.uniform(-30, 10, 1500), rng.uniform(0.5, 2.0, 1500),
+                        1 + rng.uniform(-1e-3, 1e-3, 500), 2.0 ** np.arange(-40, 40),
+                        np.nextafter(1.0, 0.0) * np.ones(1), np.nextafter(1.0, 2.0) * np.ones(1)])
+    got = _apply(emul.emul_log2, x)
+    ref = [mp.log(mp.mpf(float(v)), 2) for v in x]
+    err = np.array([float(abs(mp.mpf(float(g)) - r)) for g, r in zip(got, ref)])
+    # absolute error: <= 1.2e-16 + one rounding of the result
+    bound = 1.2e-16 + np.spacing(np.abs(got))
+    assert np.all(err <= bound), (err.max(), x[np.argmax(err - bound)])
+    assert err[(x > 0.5) & (x < 2)].max() < 2.3e-16
+    # the controller relies on log2(0) being hugely negative (the reference's `EEst == 0` branch)
+    z = _apply(emul.emul_log2, np.array([0.0, np.inf]))
+    assert z[0] <= -1000 and z[1] >= 1000
+
+
+def test_exp2_fast_accuracy(emul):
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(7)
+    y = np.concatenate([rng.uniform(-3.4, 3.4, 4000), np.arange(-3, 4), np.arange(-217, 218) / 64.0,
+                        [1 / 128, -1 / 128, 3.3999, -3.3999, 1e-300, -1e-300]])
+    got = _apply(emul.emul_exp2, y)
+    rel = np.array([float(abs(mp.mpf(float(g)) / (mp.mpf(2) ** mp.mpf(float(v))) - 1)) for g, v in zip(got, y)])
+    assert rel.max() < 2.5e-16, rel.max()
+    assert _apply(emul.emul_exp2, np.array([0.0, 1.0, -2.0])).tolist() == [1.0, 2.0, 0.25]
+
+
+def test_rcp_fast_accuracy(emul):
+    rng = np.random.default_rng(3)
+    x = 10.0 ** rng.uniform(-12, 6, 5000)
+    got = _apply(emul.emul_rcp, x)
+    assert np.max(np.abs(got * x - 1.0)) < 3e-16
+
+
+def test_short_nan_minmax_equal_julia_semantics(emul):
+    """max_abs_nan2 / min_abs_nan1 equal Base.max / Base.min of the absolute values whenever their
+    stated invariants hold (a NaN => b NaN, resp. b NaN => a NaN)."""
+    nan, inf = float("nan"), float("inf")
+    vals = [0.0, -0.0, 1.0, -1.0, 2.5, -2.5, 1e-300, -1e300, inf, -inf, nan]
+
+    def same(p, q):
+        return (math.isnan(p) and math.isnan(q)) or (p == q and math.copysign(1, p) == math.copysign(1, q))
+    for a in vals:
+        for b in vals:
+            if not (math.isnan(a) and not math.isnan(b)):      # invariant of max_abs_nan2
+                assert same(emul.emul_max_abs_nan2(a, b), emul.emul_jl_max(abs(a), abs(b))), (a, b)
+            if not (math.isnan(b) and not math.isnan(a)):      # invariant of min_abs_nan1
+                assert same(emul.emul_min_abs_nan1(a, b), emul.emul_jl_min(abs(a), abs(b))), (a, b)
