@@ -102,6 +102,18 @@ def measured_peaks():
         return {}
 
 
+def ncu_traffic(n_traj):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the headline kernel, from the
+    committed `ncu --set full` capture -- only if that capture was taken at this launch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_bench_traffic.json")))
+        if int(t["n_traj"]) == int(n_traj):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def cpu_oracle_rate(n_sample, n_threads, seconds_target=None):
     """trajectory-steps/s of the CPU oracle (C++ restatement of GPUSimpleTsit5) on a sample."""
     import oracle_lib
@@ -273,7 +285,8 @@ def main():
             "endpoint_stats": {"mean": [float(x) for x in stats["mean"]], "min": [float(x) for x in stats["min"]],
                                "max": [float(x) for x in stats["max"]], "gathered_over_ranks": world},
             "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-                         "frac": achieved / peak_nominal, "traffic": None,
+                         "frac": achieved / peak_nominal, "traffic": ncu_traffic(n),
+                         "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic = %d)" % (n * BYTES_PER_TRAJ),
                          "peak_source": "derived 148 SM x 64 FMA/clk x sm_max_mhz of MEASURED_PEAKS.json (no FP64 figure there); tensor cores n/a",
                          "peak_measured_dfma": peak_meas, "frac_of_measured_dfma": achieved / peak_meas if peak_meas else None,
                          "fp64_pipe_util": steps_per_s_gpu * FP64_INSTR_PER_STEP / (148 * 64 * sm_max * 1e6),

@@ -163,7 +163,8 @@ SDE_API int sde_system_prepare(sde_system_t sys, const sde_options_t* opt);
  *        adaptive EVERYSTEP: the time of every stored slot, same layout as out_u without the component
  *        axis ([n_traj][n_out] or [n_out][n_traj]); may be NULL.
  *        fixed step: ignored (times are trajectory independent: see sde_fixed_times).
- * naccept/nreject/retcode: [n_traj] int32, each may be NULL.
+ * naccept/nreject/retcode: [n_traj] int32, each may be NULL; fixed-step algorithms write zeros
+ *        (no step control, retcode Default).
  * devices/n_dev: CUDA device ordinals to shard over by contiguous trajectory ranges, one host
  *        thread + stream per device, no collective; NULL/0 = current device only. */
 SDE_API int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const void* p,
@@ -197,6 +198,12 @@ SDE_API int sde_probe_fma_peak(int dtype, double* tflops, double* ms);
 
 /* Number of kernels launched by this process through the library (all threads). */
 SDE_API int64_t sde_launch_count(void);
+
+/* Device buffers of sde_solve come from one stream-ordered memory pool per device, so that repeated
+ * solves do not pay cudaMalloc/cudaFree (the reference allocates per trajectory through Julia's GC;
+ * there is no counterpart to cite).  After each solve the pool keeps at most SDE_POOL_KEEP_MB
+ * (environment, default 4096) megabytes; sde_trim() returns everything to the driver. */
+SDE_API int sde_trim(void);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ COMPAT_STRICT_CONTROLLER = 2
 EXPORTS = ["sde_version", "sde_last_error", "sde_device_count", "sde_system_builtin",
            "sde_system_nvrtc", "sde_system_dims", "sde_system_free", "sde_system_prepare",
            "sde_solve", "sde_solve_device", "sde_fixed_times", "sde_host_alloc", "sde_host_free",
-           "sde_launch_count", "sde_probe_fma_peak"]
+           "sde_launch_count", "sde_probe_fma_peak", "sde_trim"]
 
 
 class SdeOptions(ctypes.Structure):

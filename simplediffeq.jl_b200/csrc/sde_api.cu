@@ -2,6 +2,7 @@
 // multi-device sharder.  See include/simplediffeq_cuda.h for the contract of every entry point.
 #include <cuda_runtime.h>
 #include <nvrtc.h>
+#include <chrono>
 
 #include <algorithm>
 #include <atomic>
@@ -329,12 +330,109 @@ void build_save_plan(int alg, const T* tgrid, int64_t n_steps, T t0, T dt, const
 }
 
 // --------------------------------------------------------------------------------------------
-// launch on the current device
+// device memory: one explicit stream-ordered pool per device.  Freed blocks stay cached in the pool
+// (release threshold = max), so repeated solves do not pay cudaMalloc / cudaFree; after a
+// host-buffer solve the pool is trimmed to SDE_POOL_KEEP_MB (default 4096 MB), and sde_trim()
+// returns everything.
+// --------------------------------------------------------------------------------------------
+std::mutex g_pool_mu;
+std::map<int, cudaMemPool_t> g_pools;
+
+int device_pool(int dev, cudaMemPool_t* out) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pools.find(dev);
+  if (it != g_pools.end()) { *out = it->second; return SDE_OK; }
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof props);
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  cudaMemPool_t pool;
+  SDE_CUDA(cudaMemPoolCreate(&pool, &props));
+  unsigned long long keep_all = ~0ULL;
+  SDE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+  g_pools[dev] = pool;
+  *out = pool;
+  return SDE_OK;
+}
+
+size_t pool_keep_bytes() {
+  const char* e = getenv("SDE_POOL_KEEP_MB");
+  const long long mb = e ? atoll(e) : 4096;
+  return (size_t)std::max<long long>(0, mb) << 20;
+}
+
+// --------------------------------------------------------------------------------------------
+// per-solve device constants (identical for every piece of a chunked solve): time grid, saveat
+// (adaptive) or save plan (fixed), plus kQueueSlots work-queue heads (one per in-flight launch)
+// --------------------------------------------------------------------------------------------
+constexpr int kQueueSlots = 4;
+
+struct SolveConsts {
+  char* scratch = nullptr;
+  const void* tgrid = nullptr;
+  const void* saveat = nullptr;
+  const int* plan_step = nullptr;
+  const void* plan_b = nullptr;
+  sde::u64* queue(int slot) const { return (sde::u64*)(scratch + 16 * slot); }
+};
+
+template <class T>
+int upload_consts_t(const sde_options_t* o, cudaMemPool_t pool, cudaStream_t st, SolveConsts* c) {
+  const bool adaptive = is_adaptive(o->alg);
+  const size_t ng = adaptive ? 0 : (size_t)o->n_steps + 1;
+  const size_t ns = o->save_mode == SDE_SAVE_SAVEAT ? (size_t)o->n_save : 0;
+  std::vector<T> tg(ng);
+  if (ng) {
+    if (o->tgrid) memcpy(tg.data(), o->tgrid, ng * sizeof(T));
+    else for (size_t k = 0; k < ng; ++k) tg[k] = (T)o->t0 + (T)((T)k * (T)o->dt);
+  }
+  std::vector<int> plan_step;
+  std::vector<T> plan_b;
+  int nb = 0;
+  if (!adaptive && ns) {
+    if (o->n_steps >= 0x7ffffffeLL) return fail(SDE_ERR_INVALID, "n_steps too large for saveat");
+    build_save_plan<T>(o->alg, tg.data(), o->n_steps, (T)o->t0, (T)o->dt, (const T*)o->saveat, o->n_save,
+                       &plan_step, &plan_b, &nb);
+  }
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t off_grid = 16 * kQueueSlots;
+  const size_t off_save = off_grid + up16(ng * sizeof(T));
+  const size_t off_pstep = off_save + up16((adaptive ? ns : 0) * sizeof(T));
+  const size_t off_pb = off_pstep + up16(plan_step.size() * sizeof(int));
+  const size_t bytes = off_pb + up16(plan_b.size() * sizeof(T));
+  SDE_CUDA(cudaMallocFromPoolAsync((void**)&c->scratch, bytes, pool, st));
+  // pageable sources are staged by the runtime before cudaMemcpyAsync returns, so the vectors may die
+  if (ng) {
+    SDE_CUDA(cudaMemcpyAsync(c->scratch + off_grid, tg.data(), ng * sizeof(T), cudaMemcpyHostToDevice, st));
+    c->tgrid = c->scratch + off_grid;
+  }
+  if (adaptive && ns) {
+    SDE_CUDA(cudaMemcpyAsync(c->scratch + off_save, o->saveat, ns * sizeof(T), cudaMemcpyHostToDevice, st));
+    c->saveat = c->scratch + off_save;
+  }
+  if (!plan_step.empty()) {
+    SDE_CUDA(cudaMemcpyAsync(c->scratch + off_pstep, plan_step.data(), plan_step.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SDE_CUDA(cudaMemcpyAsync(c->scratch + off_pb, plan_b.data(), plan_b.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    c->plan_step = (const int*)(c->scratch + off_pstep);
+    c->plan_b = c->scratch + off_pb;
+  }
+  return SDE_OK;
+}
+
+int upload_consts(const sde_options_t* o, cudaMemPool_t pool, cudaStream_t st, SolveConsts* c) {
+  return o->dtype == SDE_F64 ? upload_consts_t<double>(o, pool, st, c) : upload_consts_t<float>(o, pool, st, c);
+}
+
+// --------------------------------------------------------------------------------------------
+// launch one piece (o->n_traj trajectories) on the current device
 // --------------------------------------------------------------------------------------------
 template <class T>
-int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const void* d_u0, const void* d_p,
-             int64_t ld_in, void* d_out_u, int64_t ld_out, void* d_out_t, int32_t* d_nacc,
-             int32_t* d_nrej, int32_t* d_ret, cudaStream_t st) {
+int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const SolveConsts& c, int qslot,
+                   const void* d_u0, const void* d_p, int64_t ld_in, void* d_out_u, int64_t ld_out,
+                   void* d_out_t, int32_t* d_nacc, int32_t* d_nrej, int32_t* d_ret, cudaStream_t st) {
+  if (o->n_traj <= 0) return SDE_OK;
   const bool adaptive = is_adaptive(o->alg);
   sde::KArgs<T> a;
   memset(&a, 0, sizeof a);
@@ -353,86 +451,68 @@ int launch_t(sde_system_s* sys, const sde_options_t* o, const void* fn, const vo
   a.n_out = out_slots(o);
   a.out_t = adaptive ? (T*)d_out_t : nullptr;
   a.naccept = d_nacc; a.nreject = d_nrej; a.retcode = d_ret;
+  a.queue = c.queue(qslot);
+  a.tgrid = (const T*)c.tgrid;
+  a.saveat = (const T*)c.saveat;
+  a.plan_step = c.plan_step;
+  a.plan_b = (const T*)c.plan_b;
 
-  // small per-call device constants: queue head, time grid, saveat (adaptive) or save plan (fixed)
-  const size_t ng = adaptive ? 0 : (size_t)o->n_steps + 1;
-  const size_t ns = (size_t)a.n_save;
-  std::vector<T> tg(ng);
-  if (ng) {
-    if (o->tgrid) memcpy(tg.data(), o->tgrid, ng * sizeof(T));
-    else for (size_t k = 0; k < ng; ++k) tg[k] = (T)o->t0 + (T)((T)k * (T)o->dt);
+  int dev = 0, sms = 0, per_sm = 0;
+  SDE_CUDA(cudaGetDevice(&dev));
+  unsigned grid;
+  const int64_t full = (o->n_traj + kBlock - 1) / kBlock;
+  if (adaptive) {
+    SDE_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
+    SDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    grid = (unsigned)std::min<int64_t>(full, (int64_t)sms * per_sm);   // persistent CTAs
+  } else {
+    if (full > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
+    grid = (unsigned)full;
+    // fixed step: no step control and no failure mode -> the per-trajectory statistics are all zero
+    if (d_nacc) SDE_CUDA(cudaMemsetAsync(d_nacc, 0, 4 * (size_t)o->n_traj, st));
+    if (d_nrej) SDE_CUDA(cudaMemsetAsync(d_nrej, 0, 4 * (size_t)o->n_traj, st));
+    if (d_ret) SDE_CUDA(cudaMemsetAsync(d_ret, 0, 4 * (size_t)o->n_traj, st));
   }
-  std::vector<int> plan_step;
-  std::vector<T> plan_b;
-  int nb = 0;
-  if (!adaptive && ns) {
-    if (o->n_steps >= 0x7ffffffeLL) return fail(SDE_ERR_INVALID, "n_steps too large for saveat");
-    build_save_plan<T>(o->alg, tg.data(), o->n_steps, (T)o->t0, (T)o->dt, (const T*)o->saveat, o->n_save,
-                       &plan_step, &plan_b, &nb);
+  size_t smem = 0;
+  if (want_staged(o)) {
+    smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
+    if (smem > 48 * 1024)
+      SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t off_grid = 16;
-  const size_t off_save = off_grid + up16(ng * sizeof(T));
-  const size_t off_pstep = off_save + up16((adaptive ? ns : 0) * sizeof(T));
-  const size_t off_pb = off_pstep + up16(plan_step.size() * sizeof(int));
-  const size_t bytes = off_pb + up16(plan_b.size() * sizeof(T));
-  char* scratch = nullptr;
-  SDE_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
-  SDE_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
-  a.queue = (sde::u64*)scratch;
-  // pageable sources are staged by the runtime before cudaMemcpyAsync returns, so the vectors may die
-  if (ng) {
-    SDE_CUDA(cudaMemcpyAsync(scratch + off_grid, tg.data(), ng * sizeof(T), cudaMemcpyHostToDevice, st));
-    a.tgrid = (const T*)(scratch + off_grid);
-  }
-  if (adaptive && ns) {
-    SDE_CUDA(cudaMemcpyAsync(scratch + off_save, o->saveat, ns * sizeof(T), cudaMemcpyHostToDevice, st));
-    a.saveat = (const T*)(scratch + off_save);
-  }
-  if (!plan_step.empty()) {
-    SDE_CUDA(cudaMemcpyAsync(scratch + off_pstep, plan_step.data(), plan_step.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    SDE_CUDA(cudaMemcpyAsync(scratch + off_pb, plan_b.data(), plan_b.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-    a.plan_step = (const int*)(scratch + off_pstep);
-    a.plan_b = (const T*)(scratch + off_pb);
-  }
-
-  if (o->n_traj > 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    SDE_CUDA(cudaGetDevice(&dev));
-    unsigned grid;
-    const int64_t full = (o->n_traj + kBlock - 1) / kBlock;
-    if (adaptive) {
-      SDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
-      if (per_sm < 1) per_sm = 1;
-      grid = (unsigned)std::min<int64_t>(full, (int64_t)sms * per_sm);   // persistent CTAs
-    } else {
-      if (full > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
-      grid = (unsigned)full;
-    }
-    size_t smem = 0;
-    if (want_staged(o)) {
-      smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
-      if (smem > 48 * 1024)
-        SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    void* params[] = {&a};
-    SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, smem, st));
-    g_launches.fetch_add(1);
-  }
-  SDE_CUDA(cudaFreeAsync(scratch, st));
+  void* params[] = {&a};
+  SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, smem, st));
+  g_launches.fetch_add(1);
   return SDE_OK;
 }
 
+int launch_piece(sde_system_s* sys, const sde_options_t* o, const void* fn, const SolveConsts& c, int qslot,
+                 const void* d_u0, const void* d_p, int64_t ld_in, void* d_out_u, int64_t ld_out,
+                 void* d_out_t, int32_t* d_nacc, int32_t* d_nrej, int32_t* d_ret, cudaStream_t st) {
+  if (o->dtype == SDE_F64)
+    return launch_piece_t<double>(sys, o, fn, c, qslot, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+  return launch_piece_t<float>(sys, o, fn, c, qslot, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+}
+
+// device-resident solve: constants + one launch on the caller's stream
 int launch(sde_system_s* sys, const sde_options_t* o, const void* d_u0, const void* d_p, int64_t ld_in,
            void* d_out_u, int64_t ld_out, void* d_out_t, int32_t* d_nacc, int32_t* d_nrej,
            int32_t* d_ret, cudaStream_t st) {
   const void* fn = nullptr;
   int rc = get_kernel(sys, o, true, &fn);
   if (rc != SDE_OK) return rc;
-  if (o->dtype == SDE_F64)
-    return launch_t<double>(sys, o, fn, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
-  return launch_t<float>(sys, o, fn, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+  int dev = 0;
+  SDE_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  rc = device_pool(dev, &pool);
+  if (rc != SDE_OK) return rc;
+  SolveConsts c;
+  rc = upload_consts(o, pool, st, &c);
+  if (rc == SDE_OK)
+    rc = launch_piece(sys, o, fn, c, 0, d_u0, d_p, ld_in, d_out_u, ld_out, d_out_t, d_nacc, d_nrej, d_ret, st);
+  if (c.scratch) cudaFreeAsync(c.scratch, st);
+  return rc;
 }
 
 
@@ -464,78 +544,144 @@ struct RangeSource {
   int64_t max_piece() const { return shared ? std::min(grain, total) : hi - lo; }
 };
 
-// one device of a host-buffer solve
+// one device of a host-buffer solve.
+// The device's range is cut into pieces; piece i uses buffer set i % 2 on stream i % 2, each stream
+// running H2D -> kernel -> D2H in order, so the copies of one piece overlap the kernel of its
+// neighbour and the next kernel's CTAs fill the SMs the previous kernel's tail leaves idle.
 int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSource src,
                 const char* u0, const char* p, char* out_u, char* out_t, int32_t* nacc, int32_t* nrej,
                 int32_t* ret, std::string* err) {
+  constexpr int kBuf = 2;
+  struct Buffers {
+    char *u0 = nullptr, *p = nullptr, *out = nullptr, *t = nullptr;
+    int32_t *na = nullptr, *nr = nullptr, *rc = nullptr;
+  };
   auto body = [&]() -> int {
     if (device >= 0) SDE_CUDA(cudaSetDevice(device));
+    int dev = 0;
+    SDE_CUDA(cudaGetDevice(&dev));
     const size_t es = esize(o->dtype);
     const int N = sys->n_state, NP = sys->n_param;
     const int64_t n_all = o->n_traj, slots = out_slots(o);
     const bool series = o->save_mode != SDE_SAVE_ENDPOINT;
     const bool adaptive = is_adaptive(o->alg);
-    // device memory budget per chunk: keep well below HBM capacity
+    const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
+    // SDE_TRACE=1: wall-clock phases of the host-buffer path on stderr (adds stream syncs)
+    const bool trace = getenv("SDE_TRACE") != nullptr;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point a) {
+      return std::chrono::duration<double, std::milli>(now() - a).count();
+    };
+    auto t_phase = now();
+    const void* fn = nullptr;
+    int rc = get_kernel(sys, o, true, &fn);
+    if (rc != SDE_OK) return rc;
+    cudaMemPool_t pool;
+    rc = device_pool(dev, &pool);
+    if (rc != SDE_OK) return rc;
+
+    // piece size: a quarter of the range (at least 2^17 trajectories), bounded by the memory budget
+    // (60 % of what is free now plus what the pool already holds, shared by the kBuf buffer sets)
     size_t free_b = 0, total_b = 0;
     SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_traj = es * ((size_t)N + NP + (size_t)(N + 1) * slots + 1) + 12;
-    int64_t chunk = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
-    chunk = std::min<int64_t>(chunk, src.max_piece());
-    if (chunk > 32) chunk -= chunk % 32;
-    cudaStream_t st;
-    SDE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    char *d_u0 = nullptr, *d_p = nullptr, *d_out = nullptr, *d_t = nullptr;
-    int32_t *d_na = nullptr, *d_nr = nullptr, *d_rc = nullptr;
-    int rc = SDE_OK;
+    unsigned long long pooled = 0, pool_used = 0;   // idle bytes the pool already holds count as free
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &pooled);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &pool_used);
+    pooled = pooled > pool_used ? pooled - pool_used : 0;
+    const size_t per_traj = es * ((size_t)N + NP + (size_t)N * slots + (t_series ? slots : 1)) + 12;
+    int64_t piece = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)(free_b + pooled)) / per_traj / kBuf);
+    const int64_t range = src.max_piece();
+    int64_t want = std::max<int64_t>((range + 3) / 4, (int64_t)1 << 17);
+    if (const char* e = getenv("SDE_TUNE_PIECE")) want = std::max<int64_t>(32, atoll(e));   // measurement only
+    piece = std::min<int64_t>(piece, std::min<int64_t>(want, range));
+    if (piece > 32) piece = (piece + 31) & ~(int64_t)31;
+    const int n_buf = piece >= range ? 1 : kBuf;
+
+    cudaStream_t st[kBuf] = {nullptr, nullptr};
+    Buffers buf[kBuf];
+    SolveConsts consts;
     auto cleanup = [&]() {
-      cudaFree(d_u0); cudaFree(d_p); cudaFree(d_out); cudaFree(d_t); cudaFree(d_na); cudaFree(d_nr); cudaFree(d_rc);
-      cudaStreamDestroy(st);
+      for (int b = 0; b < kBuf; ++b) if (st[b]) cudaStreamSynchronize(st[b]);   // nothing in flight uses the buffers
+      for (int b = 0; b < kBuf; ++b) {
+        if (!st[b]) continue;
+        Buffers& B = buf[b];
+        void* ptrs[] = {B.u0, B.p, B.out, B.t, B.na, B.nr, B.rc};
+        for (void* q : ptrs) if (q) cudaFreeAsync(q, st[b]);
+      }
+      if (consts.scratch && st[0]) cudaFreeAsync(consts.scratch, st[0]);
+      for (int b = 0; b < kBuf; ++b) if (st[b]) { cudaStreamSynchronize(st[b]); cudaStreamDestroy(st[b]); }
+      cudaMemPoolTrimTo(pool, pool_keep_bytes());
     };
 #define SDE_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
       return fail(SDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
-    if (chunk > 0) {
-      SDE_TRY(cudaMalloc((void**)&d_u0, es * N * chunk));
-      if (NP) SDE_TRY(cudaMalloc((void**)&d_p, es * NP * chunk));
-      SDE_TRY(cudaMalloc((void**)&d_out, es * N * slots * chunk));
-      const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
-      if (adaptive && out_t) SDE_TRY(cudaMalloc((void**)&d_t, es * chunk * (t_series ? slots : 1)));
-      if (nacc) SDE_TRY(cudaMalloc((void**)&d_na, 4 * chunk));
-      if (nrej) SDE_TRY(cudaMalloc((void**)&d_nr, 4 * chunk));
-      if (ret) SDE_TRY(cudaMalloc((void**)&d_rc, 4 * chunk));
+    if (piece <= 0) return SDE_OK;
+    for (int b = 0; b < n_buf; ++b) {
+      SDE_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+      Buffers& B = buf[b];
+      SDE_TRY(cudaMallocFromPoolAsync((void**)&B.u0, es * N * piece, pool, st[b]));
+      if (NP) SDE_TRY(cudaMallocFromPoolAsync((void**)&B.p, es * NP * piece, pool, st[b]));
+      SDE_TRY(cudaMallocFromPoolAsync((void**)&B.out, es * N * slots * piece, pool, st[b]));
+      if (adaptive && out_t) SDE_TRY(cudaMallocFromPoolAsync((void**)&B.t, es * piece * (t_series ? slots : 1), pool, st[b]));
+      if (nacc) SDE_TRY(cudaMallocFromPoolAsync((void**)&B.na, 4 * piece, pool, st[b]));
+      if (nrej) SDE_TRY(cudaMallocFromPoolAsync((void**)&B.nr, 4 * piece, pool, st[b]));
+      if (ret) SDE_TRY(cudaMallocFromPoolAsync((void**)&B.rc, 4 * piece, pool, st[b]));
+    }
+    // constants once, on stream 0; the other stream waits for them
+    rc = upload_consts(o, pool, st[0], &consts);
+    if (rc != SDE_OK) { cleanup(); return rc; }
+    if (n_buf > 1) {
+      cudaEvent_t ready;
+      SDE_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+      cudaEventRecord(ready, st[0]);
+      cudaStreamWaitEvent(st[1], ready, 0);
+      cudaEventDestroy(ready);
+    }
+    if (trace) {
+      for (int b = 0; b < n_buf; ++b) cudaStreamSynchronize(st[b]);
+      fprintf(stderr, "[sde trace] dev %d: setup (piece %lld x %d buffers, pool held %.1f MB) %.3f ms\n", dev,
+              (long long)piece, n_buf, (double)pooled / 1048576.0, ms_since(t_phase));
     }
     int64_t c0 = 0, c1 = 0;
-    while (chunk > 0 && src.next(chunk, &c0, &c1)) {
+    for (int i = 0; src.next(piece, &c0, &c1); ++i) {
+      const int b = i % n_buf;
+      const Buffers& B = buf[b];
+      cudaStream_t s_ = st[b];
       const int64_t n = c1 - c0;
-      // H2D: SoA rows of the shard (host pitch = n_all elements, device pitch = chunk elements)
-      SDE_TRY(cudaMemcpy2DAsync(d_u0, es * chunk, u0 + es * c0, es * n_all, es * n, N, cudaMemcpyHostToDevice, st));
-      if (NP) SDE_TRY(cudaMemcpy2DAsync(d_p, es * chunk, p + es * c0, es * n_all, es * n, NP, cudaMemcpyHostToDevice, st));
+      t_phase = now();
+      // H2D: SoA rows of the piece (host pitch = n_all elements, device pitch = piece elements)
+      SDE_TRY(cudaMemcpy2DAsync(B.u0, es * piece, u0 + es * c0, es * n_all, es * n, N, cudaMemcpyHostToDevice, s_));
+      if (NP) SDE_TRY(cudaMemcpy2DAsync(B.p, es * piece, p + es * c0, es * n_all, es * n, NP, cudaMemcpyHostToDevice, s_));
+      if (trace) { cudaStreamSynchronize(s_); fprintf(stderr, "[sde trace] dev %d: [%lld,%lld) H2D %.3f ms\n", dev, (long long)c0, (long long)c1, ms_since(t_phase)); t_phase = now(); }
       sde_options_t oc = *o;
       oc.n_traj = n;
-      rc = launch(sys, &oc, d_u0, d_p, chunk, d_out, chunk, d_t, d_na, d_nr, d_rc, st);
+      rc = launch_piece(sys, &oc, fn, consts, b, B.u0, B.p, piece, B.out, piece, B.t, B.na, B.nr, B.rc, s_);
       if (rc != SDE_OK) { cleanup(); return rc; }
+      if (trace) { cudaStreamSynchronize(s_); fprintf(stderr, "[sde trace] dev %d: [%lld,%lld) kernel %.3f ms\n", dev, (long long)c0, (long long)c1, ms_since(t_phase)); t_phase = now(); }
       // D2H
       if (!series) {
-        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, d_out, es * chunk, es * n, N, cudaMemcpyDeviceToHost, st));
+        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, B.out, es * piece, es * n, N, cudaMemcpyDeviceToHost, s_));
       } else if (o->layout == SDE_LAYOUT_TRAJ_MAJOR) {
-        SDE_TRY(cudaMemcpyAsync(out_u + es * N * slots * c0, d_out, es * N * slots * n, cudaMemcpyDeviceToHost, st));
+        SDE_TRY(cudaMemcpyAsync(out_u + es * N * slots * c0, B.out, es * N * slots * n, cudaMemcpyDeviceToHost, s_));
       } else {
-        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, d_out, es * chunk, es * n, (size_t)N * slots, cudaMemcpyDeviceToHost, st));
+        SDE_TRY(cudaMemcpy2DAsync(out_u + es * c0, es * n_all, B.out, es * piece, es * n, (size_t)N * slots, cudaMemcpyDeviceToHost, s_));
       }
-      if (d_t) {
-        const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
-        if (!t_series) SDE_TRY(cudaMemcpyAsync(out_t + es * c0, d_t, es * n, cudaMemcpyDeviceToHost, st));
+      if (B.t) {
+        if (!t_series) SDE_TRY(cudaMemcpyAsync(out_t + es * c0, B.t, es * n, cudaMemcpyDeviceToHost, s_));
         else if (o->layout == SDE_LAYOUT_TRAJ_MAJOR)
-          SDE_TRY(cudaMemcpyAsync(out_t + es * slots * c0, d_t, es * slots * n, cudaMemcpyDeviceToHost, st));
+          SDE_TRY(cudaMemcpyAsync(out_t + es * slots * c0, B.t, es * slots * n, cudaMemcpyDeviceToHost, s_));
         else
-          SDE_TRY(cudaMemcpy2DAsync(out_t + es * c0, es * n_all, d_t, es * chunk, es * n, (size_t)slots, cudaMemcpyDeviceToHost, st));
+          SDE_TRY(cudaMemcpy2DAsync(out_t + es * c0, es * n_all, B.t, es * piece, es * n, (size_t)slots, cudaMemcpyDeviceToHost, s_));
       }
-      if (d_na) SDE_TRY(cudaMemcpyAsync(nacc + c0, d_na, 4 * n, cudaMemcpyDeviceToHost, st));
-      if (d_nr) SDE_TRY(cudaMemcpyAsync(nrej + c0, d_nr, 4 * n, cudaMemcpyDeviceToHost, st));
-      if (d_rc) SDE_TRY(cudaMemcpyAsync(ret + c0, d_rc, 4 * n, cudaMemcpyDeviceToHost, st));
-      SDE_TRY(cudaStreamSynchronize(st));
+      if (B.na) SDE_TRY(cudaMemcpyAsync(nacc + c0, B.na, 4 * n, cudaMemcpyDeviceToHost, s_));
+      if (B.nr) SDE_TRY(cudaMemcpyAsync(nrej + c0, B.nr, 4 * n, cudaMemcpyDeviceToHost, s_));
+      if (B.rc) SDE_TRY(cudaMemcpyAsync(ret + c0, B.rc, 4 * n, cudaMemcpyDeviceToHost, s_));
+      if (trace) { cudaStreamSynchronize(s_); fprintf(stderr, "[sde trace] dev %d: [%lld,%lld) D2H %.3f ms\n", dev, (long long)c0, (long long)c1, ms_since(t_phase)); }
     }
+    for (int b = 0; b < n_buf; ++b) SDE_TRY(cudaStreamSynchronize(st[b]));
 #undef SDE_TRY
+    t_phase = now();
     cleanup();
+    if (trace) fprintf(stderr, "[sde trace] dev %d: release + trim %.3f ms\n", dev, ms_since(t_phase));
     return SDE_OK;
   };
   int rc = body();
@@ -726,5 +872,14 @@ int sde_host_free(void* ptr) {
 }
 
 int64_t sde_launch_count(void) { return g_launches.load(); }
+
+int sde_trim(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto& kv : g_pools) {
+    cudaError_t e = cudaMemPoolTrimTo(kv.second, 0);
+    if (e != cudaSuccess) return fail(SDE_ERR_CUDA, "cudaMemPoolTrimTo: %s", cudaGetErrorString(e));
+  }
+  return SDE_OK;
+}
 
 }  // extern "C"
