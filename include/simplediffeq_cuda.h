@@ -205,6 +205,73 @@ SDE_API int64_t sde_launch_count(void);
  * (environment, default 4096) megabytes; sde_trim() returns everything to the driver. */
 SDE_API int sde_trim(void);
 
+/* ============================================================================================
+ * SimpleEM: fixed-step Euler-Maruyama ensembles for SDEs du = f(u,p,t) dt + g(u,p,t) dW.
+ * Replaces `DiffEqBase.solve(prob::SDEProblem{uType,tType,false}, alg::SimpleEM; dt)`
+ * (src/euler_maruyama.jl:48-94, the out-of-place method), called once per trajectory by the
+ * reference's ensemble driver.  n_steps = Int((tspan[2]-tspan[1])/dt) (:66) is computed by the host
+ * layer (Julia raises InexactError when the quotient is not an integer); the states are
+ * t_i = muladd(i, dt, t0) (:68).  The reference keeps every state (:67): SDE_SAVE_EVERYSTEP gives
+ * n_steps + 1 slots per trajectory (slot 0 = u0), SDE_SAVE_ENDPOINT only the last one.
+ *
+ * Noise: the reference calls randn() on Julia's task-local RNG (:77,:80,:84), which cannot be
+ * reproduced outside that process.  SDE_NOISE_PHILOX draws the increments from Philox4x32-10 keyed
+ * by `seed` and counted by (traj_offset + trajectory index, step, component) -- see
+ * csrc/device/sde_em.cuh for the exact layout -- so results do not depend on devices, pieces or
+ * launch geometry; SDE_NOISE_PROVIDED reads standard normals from the caller:
+ * noise[(step * n_noise + m)][trajectory] (SoA).  sde_em_noise() returns the normals a PHILOX solve
+ * with the same options consumes, in that layout.
+ * ============================================================================================ */
+typedef struct sde_em_system_s* sde_em_system_t;
+
+#define SDE_NOISE_PHILOX 0
+#define SDE_NOISE_PROVIDED 1
+
+typedef struct sde_em_options {
+  int32_t dtype;        /* SDE_F64 | SDE_F32 */
+  int32_t save_mode;    /* SDE_SAVE_EVERYSTEP (the reference) | SDE_SAVE_ENDPOINT */
+  int32_t layout;       /* SDE_SAVE_EVERYSTEP output: SDE_LAYOUT_TRAJ_MAJOR | SDE_LAYOUT_SOA */
+  int32_t noise_mode;   /* SDE_NOISE_PHILOX | SDE_NOISE_PROVIDED */
+  int64_t n_traj;
+  double t0, dt;
+  int64_t n_steps;
+  uint64_t seed;        /* PHILOX key */
+  int64_t traj_offset;  /* global index of trajectory 0 (PHILOX counter); 0 for a whole ensemble */
+} sde_em_options_t;
+
+/* Built-in SDE systems: "gbm" (f = p1*u, g = p2*u; the docstring example src/euler_maruyama.jl:27-28),
+ * "linadd1" / "linadd2" (f = p1*u, g = p2; test/simpleem_tests.jl:4-5,16, scalar / 2 components),
+ * "ou" (f = p1*(p2-u), g = p3), "nondiag2x4" (f = p1.*u, G = the 2x4 matrix of test/simpleem_tests.jl:33-47). */
+SDE_API int sde_em_system_builtin(const char* name, sde_em_system_t* out);
+
+/* User SDE: CUDA-C source defining
+ *     __device__ void rhs  (real* f, const real* u, const real* p, real t);   // drift, n_state values
+ *     __device__ void noise(real* g, const real* u, const real* p, real t);   // diagonal: n_state values;
+ *                                                                              // else n_state x n_noise, row major
+ * compiled by NVRTC for sm_100a with --fmad=false (replaces prob.f / prob.g). */
+SDE_API int sde_em_system_nvrtc(const char* src, int n_state, int n_param, int n_noise, int diagonal,
+                                sde_em_system_t* out, char* log, size_t log_len);
+SDE_API int sde_em_system_dims(sde_em_system_t sys, int* n_state, int* n_param, int* n_noise, int* diagonal);
+SDE_API void sde_em_system_free(sde_em_system_t sys);
+SDE_API int sde_em_system_prepare(sde_em_system_t sys, const sde_em_options_t* opt);
+
+/* Host buffers: u0 [n_state][n_traj], p [n_param][n_traj] (SoA); noise (PROVIDED only, else NULL)
+ * [n_steps * n_noise][n_traj]; out_u: ENDPOINT [n_state][n_traj], EVERYSTEP n_steps+1 slots per
+ * trajectory in opt->layout.  devices/n_dev as in sde_solve (contiguous ranges, no collective). */
+SDE_API int sde_em_solve(sde_em_system_t sys, const sde_em_options_t* opt, const void* u0, const void* p,
+                         const void* noise, void* out_u, const int* devices, int n_dev);
+
+/* Device-resident buffers on the current device (ld_* = component strides, as in sde_solve_device). */
+SDE_API int sde_em_solve_device(sde_em_system_t sys, const sde_em_options_t* opt, const void* d_u0,
+                                const void* d_p, int64_t ld_in, const void* d_noise, int64_t noise_ld,
+                                void* d_out_u, int64_t ld_out, void* stream, int async);
+
+/* The standard normals of the PHILOX stream: out[(step * n_noise + m)][trajectory] for the opt's
+ * (dtype, seed, traj_offset, n_traj, n_steps); host array / device array with row stride ld. */
+SDE_API int sde_em_noise(const sde_em_options_t* opt, int n_noise, void* out);
+SDE_API int sde_em_noise_device(const sde_em_options_t* opt, int n_noise, void* d_out, int64_t ld, void* stream,
+                                int async);
+
 #ifdef __cplusplus
 }
 #endif

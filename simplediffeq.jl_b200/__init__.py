@@ -8,9 +8,13 @@ from .api import (CudaRHS, EnsembleProblem, EnsembleSolution, GPUSimpleATsit5, G
                   GPUSimpleAVern9, GPUSimpleEuler, GPUSimpleRK4, GPUSimpleTsit5, GPUSimpleVern7, GPUSimpleVern9,
                   ODEProblem, ODESolution, System, builtin_system, remake, solve, solve_arrays,
                   solve_device, systems)
+from .em import (CudaSDE, EMEnsembleSolution, SDEProblem, SDESystem, SimpleEM, em_noise, em_steps, em_times,
+                 sde_systems, solve_em, solve_em_arrays, solve_em_device)
 from .jlrange import JuliaRange, jl_range
 
 __all__ = ["CudaRHS", "EnsembleProblem", "EnsembleSolution", "GPUSimpleATsit5", "GPUSimpleAVern7",
            "GPUSimpleAVern9", "GPUSimpleEuler", "GPUSimpleRK4", "GPUSimpleTsit5", "GPUSimpleVern7", "GPUSimpleVern9",
            "ODEProblem", "ODESolution", "System", "builtin_system", "remake", "solve", "solve_arrays",
-           "solve_device", "systems", "JuliaRange", "jl_range"]
+           "solve_device", "systems", "JuliaRange", "jl_range",
+           "CudaSDE", "EMEnsembleSolution", "SDEProblem", "SDESystem", "SimpleEM", "em_noise", "em_steps", "em_times",
+           "sde_systems", "solve_em", "solve_em_arrays", "solve_em_device"]

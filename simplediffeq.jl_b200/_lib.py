@@ -23,7 +23,9 @@ COMPAT_STRICT_CONTROLLER = 2
 EXPORTS = ["sde_version", "sde_last_error", "sde_device_count", "sde_system_builtin",
            "sde_system_nvrtc", "sde_system_dims", "sde_system_free", "sde_system_prepare",
            "sde_solve", "sde_solve_device", "sde_fixed_times", "sde_host_alloc", "sde_host_free",
-           "sde_launch_count", "sde_probe_fma_peak", "sde_trim"]
+           "sde_launch_count", "sde_probe_fma_peak", "sde_trim",
+           "sde_em_system_builtin", "sde_em_system_nvrtc", "sde_em_system_dims", "sde_em_system_free",
+           "sde_em_system_prepare", "sde_em_solve", "sde_em_solve_device", "sde_em_noise", "sde_em_noise_device"]
 
 
 class SdeOptions(ctypes.Structure):
@@ -33,6 +35,16 @@ class SdeOptions(ctypes.Structure):
                 ("dt", ctypes.c_double), ("abstol", ctypes.c_double), ("reltol", ctypes.c_double),
                 ("n_steps", ctypes.c_int64), ("tgrid", ctypes.c_void_p), ("saveat", ctypes.c_void_p),
                 ("n_save", ctypes.c_int64), ("max_attempts", ctypes.c_int64), ("out_capacity", ctypes.c_int64)]
+
+
+class SdeEmOptions(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int32), ("save_mode", ctypes.c_int32), ("layout", ctypes.c_int32),
+                ("noise_mode", ctypes.c_int32), ("n_traj", ctypes.c_int64), ("t0", ctypes.c_double),
+                ("dt", ctypes.c_double), ("n_steps", ctypes.c_int64), ("seed", ctypes.c_uint64),
+                ("traj_offset", ctypes.c_int64)]
+
+
+NOISE_PHILOX, NOISE_PROVIDED = 0, 1
 
 
 class SdeError(RuntimeError):
@@ -71,12 +83,25 @@ def lib():
                                    ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int]
     L.sde_fixed_times.argtypes = [ctypes.POINTER(SdeOptions), vp, ctypes.c_int64,
                                   ctypes.POINTER(ctypes.c_int64)]
+    emo = ctypes.POINTER(SdeEmOptions)
+    L.sde_em_system_builtin.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.sde_em_system_nvrtc.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_size_t]
+    L.sde_em_system_dims.argtypes = [vp] + [ctypes.POINTER(ctypes.c_int)] * 4
+    L.sde_em_system_free.argtypes = [vp]
+    L.sde_em_system_free.restype = None
+    L.sde_em_system_prepare.argtypes = [vp, emo]
+    L.sde_em_solve.argtypes = [vp, emo, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L.sde_em_solve_device.argtypes = [vp, emo, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_int64,
+                                      vp, ctypes.c_int]
+    L.sde_em_noise.argtypes = [emo, ctypes.c_int, vp]
+    L.sde_em_noise_device.argtypes = [emo, ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int]
     L.sde_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.sde_host_free.argtypes = [vp]
     L.sde_launch_count.restype = ctypes.c_int64
     L.sde_probe_fma_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     for name in EXPORTS:
-        if name not in ("sde_last_error", "sde_system_free", "sde_launch_count", "sde_version"):
+        if name not in ("sde_last_error", "sde_system_free", "sde_em_system_free", "sde_launch_count", "sde_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

@@ -307,6 +307,10 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
     ordinals) shards the ensemble by contiguous index ranges; `layout` ("traj_major" | "soa")
     selects the memory layout of series outputs; `maxiters` (0 = unlimited like the reference)
     bounds adaptive attempts per trajectory."""
+    from . import em as _em
+    if isinstance(alg, _em.SimpleEM):     # SDEProblem + SimpleEM: src/euler_maruyama.jl:48-94
+        return _em.solve_em(prob, alg, dt=dt, trajectories=trajectories, save_everystep=save_everystep,
+                            devices=devices, layout=layout, **kwargs)
     if isinstance(prob, ODEProblem):
         ens = EnsembleProblem(prob)
         trajectories = 1

@@ -1,0 +1,244 @@
+// sde_em.cuh -- ensemble Euler-Maruyama (the reference's SimpleEM, src/euler_maruyama.jl:48-94,
+// out-of-place method) for sm_100a: one trajectory per thread, state in registers, every state of a
+// trajectory optionally stored (the reference keeps all of them, :67).
+//
+// Noise.  The reference draws `randn(typeof(u0))` from Julia's task-local RNG (:77,:80,:84), which no
+// other process can reproduce.  Here the increments come from a COUNTER-BASED generator, so that a
+// trajectory's noise depends only on (seed, global trajectory index, step, component) -- never on the
+// launch geometry, the device count or how the ensemble was cut into pieces:
+//   the normal with linear index q = step*M + m of global trajectory g is element q % K of Philox4x32-10
+//   block b = q / K (K = 2 for double, 4 for float), counter (g_lo, g_hi, b_lo, b_hi), key (seed_lo, seed_hi);
+//   double: a = r0 | r1<<32, c = r2 | r3<<32, u1 = ((a>>11)+1) 2^-53 in (0,1], u2 = (c>>11) 2^-53 in [0,1),
+//           rad = sqrt(-2 ln u1), z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2)          (Box-Muller)
+//   float : (r0,r1) and (r2,r3): u1 = ((r>>8)+1) 2^-24, u2 = (r'>>8) 2^-24, same transform
+// or (kNoiseProvided) from a caller-supplied array noise[(step*M + m) * noise_ld + traj], which is how
+// the parity tests feed the kernel and the CPU oracle the same increments.
+//
+// Step arithmetic = the reference's @muladd rewriting (oracle/oracle_em.cpp states the derivation):
+//   scalar            u = fma(sqdt*g, z, fma(f, dt, uprev))                       (:76-77)
+//   vector diagonal   u_c = fma(f_c, dt, uprev_c + (sqdt*g_c)*z_c)                (:79-80)
+//   non-diagonal      u_i = (sum_j (sqdt*G_ij)*z_j, left to right) + fma(f_i, dt, uprev_i)   (:83-84, A11)
+//   tprev = fma(i, dt, t0) (:68), sqdt = sqrt(dt) (:69)
+#pragma once
+#include "sde_common.cuh"
+
+namespace sde {
+
+enum NoiseMode { kNoisePhilox = 0, kNoiseProvided = 1 };
+
+template <class T>
+struct EMArgs {
+  const T* u0;        // SoA u0[c * ld_in + i]
+  const T* p;         // SoA p [c * ld_in + i]
+  i64 n_traj;         // trajectories of this launch
+  i64 ld_in;
+  T t0, dt;
+  i64 n_steps;        // states per trajectory = n_steps + 1
+  int layout;
+  T* out_u;           // endpoint: SoA out_u[c * ld_out + i]; every step: n_steps + 1 slots, layout as KArgs
+  i64 ld_out;
+  u64 seed;
+  i64 traj_offset;    // global index of trajectory 0 of this launch (Philox counter)
+  const T* noise;     // kNoiseProvided: noise[(step*M + m) * noise_ld + i]
+  i64 noise_ld;
+};
+
+// ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) ------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                              unsigned k0, unsigned k1, unsigned* r) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
+template <class T> struct NormalBlock;
+template <> struct NormalBlock<double> {
+  static constexpr int K = 2;
+  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, double* z) {
+    unsigned r[4];
+    philox4x32_10((unsigned)traj, (unsigned)(traj >> 32), (unsigned)b, (unsigned)(b >> 32),
+                  (unsigned)seed, (unsigned)(seed >> 32), r);
+    const u64 a = (u64)r[0] | ((u64)r[1] << 32), c = (u64)r[2] | ((u64)r[3] << 32);
+    const double u1 = (double)((a >> 11) + 1ull) * 1.1102230246251565e-16;   // 2^-53, (0,1]
+    const double u2 = (double)(c >> 11) * 1.1102230246251565e-16;            // [0,1)
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z[0] = rad * cs;
+    z[1] = rad * sn;
+  }
+};
+template <> struct NormalBlock<float> {
+  static constexpr int K = 4;
+  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, float* z) {
+    unsigned r[4];
+    philox4x32_10((unsigned)traj, (unsigned)(traj >> 32), (unsigned)b, (unsigned)(b >> 32),
+                  (unsigned)seed, (unsigned)(seed >> 32), r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = (float)((r[2 * h] >> 8) + 1u) * 5.9604644775390625e-8f;   // 2^-24, (0,1]
+      const float u2 = (float)(r[2 * h + 1] >> 8) * 5.9604644775390625e-8f;      // [0,1)
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z[2 * h] = rad * cs;
+      z[2 * h + 1] = rad * sn;
+    }
+  }
+};
+
+// sequential reader of one trajectory's normal stream (linear index q = step*M + m)
+template <class T, int NOISE>
+struct NoiseStream {
+  static constexpr int K = NormalBlock<T>::K;
+  const EMArgs<T>& a;
+  i64 traj;      // local index
+  i64 q;
+  T z[K];
+  __device__ __forceinline__ NoiseStream(const EMArgs<T>& a_, i64 traj_) : a(a_), traj(traj_), q(0) {}
+  __device__ __forceinline__ T next() {
+    T v;
+    if (NOISE == kNoiseProvided) {
+      v = a.noise[q * a.noise_ld + traj];
+    } else {
+      const int k = (int)(q % K);
+      if (k == 0) NormalBlock<T>::make(a.seed, (u64)(a.traj_offset + traj), (u64)(q / K), z);
+      v = z[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) if (k == j) v = z[j];
+    }
+    ++q;
+    return v;
+  }
+};
+
+template <class T, int N>
+__device__ __forceinline__ void em_put(const EMArgs<T>& a, i64 traj, i64 slot, const T* v) {
+  if (a.layout == kLayoutTrajMajor) {
+    T* o = a.out_u + (traj * (a.n_steps + 1) + slot) * N;
+#pragma unroll
+    for (int c = 0; c < N; ++c) o[c] = v[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < N; ++c) a.out_u[(slot * N + c) * a.ld_out + traj] = v[c];
+  }
+}
+
+// SAVE: kSaveEndpoint | kSaveEveryStep (the reference's behaviour)
+template <class Sys, class T, int SAVE, int NOISE>
+__device__ __forceinline__ void em_body(const EMArgs<T>& a) {
+  constexpr int N = Sys::N, NP = Sys::NP, M = Sys::M;
+  constexpr bool kDiag = Sys::kDiagonal;
+  const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (traj >= a.n_traj) return;
+  T u[N], p[NP > 0 ? NP : 1];
+#pragma unroll
+  for (int c = 0; c < N; ++c) u[c] = a.u0[(i64)c * a.ld_in + traj];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) p[c] = a.p[(i64)c * a.ld_in + traj];
+  const T dt = a.dt;
+  const T sqdt = sde_sqrt(dt);
+  NoiseStream<T, NOISE> ns(a, traj);
+  if (SAVE == kSaveEveryStep) em_put<T, N>(a, traj, 0, u);
+  for (i64 s = 0; s < a.n_steps; ++s) {
+    const T tprev = fma((T)s, dt, a.t0);
+    T f[N], g[kDiag ? N : N * M], z[M];
+    Sys::rhs(f, u, p, tprev);
+    Sys::noise(g, u, p, tprev);
+#pragma unroll
+    for (int m = 0; m < M; ++m) z[m] = ns.next();
+    if (kDiag && N == 1) {
+      u[0] = fma(sqdt * g[0], z[0], fma(f[0], dt, u[0]));
+    } else if (kDiag) {
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        const T odd = u[c] + (sqdt * g[c]) * z[c];
+        u[c] = fma(f[c], dt, odd);
+      }
+    } else {
+      T un[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        T acc = (sqdt * g[i * M]) * z[0];
+#pragma unroll
+        for (int j = 1; j < M; ++j) acc = acc + (sqdt * g[i * M + j]) * z[j];
+        un[i] = acc + fma(f[i], dt, u[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) u[i] = un[i];
+    }
+    if (SAVE == kSaveEveryStep) em_put<T, N>(a, traj, s + 1, u);
+  }
+  if (SAVE == kSaveEndpoint) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) a.out_u[(i64)c * a.ld_out + traj] = u[c];
+  }
+}
+
+// writes the normals a kNoisePhilox solve with the same (seed, traj_offset) consumes:
+// out[(step*M + m) * ld + traj]
+template <class T>
+__device__ __forceinline__ void em_noise_body(u64 seed, i64 traj_offset, i64 n_traj, i64 n_normals, T* out, i64 ld) {
+  constexpr int K = NormalBlock<T>::K;
+  const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (traj >= n_traj) return;
+  T z[K];
+  for (i64 b = 0; b * K < n_normals; ++b) {
+    NormalBlock<T>::make(seed, (u64)(traj_offset + traj), (u64)b, z);
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (b * K + j < n_normals) out[(b * K + j) * ld + traj] = z[j];
+  }
+}
+
+// ---- built-in SDE systems (drift rhs + diffusion noise) -------------------------------------------
+//   gbm         docstring example src/euler_maruyama.jl:27-28: f = p1*u, g = p2*u (0.1u, 0.2u)
+//   linadd1/2   test/simpleem_tests.jl:4-5,16: f = p1*u (2u), g = p2 (1), scalar / SVector{2}
+//   ou          Ornstein-Uhlenbeck (not in the reference): f = p1*(p2 - u), g = p3
+//   nondiag2x4  test/simpleem_tests.jl:33-47: f = p1 .* u (1.01), G = the test's 2x4 matrix
+struct EmGBM {
+  static constexpr int N = 1, NP = 2, M = 1;
+  static constexpr bool kDiagonal = true;
+  template <class T> __device__ __forceinline__ static void rhs(T* f, const T* u, const T* p, T) { f[0] = p[0] * u[0]; }
+  template <class T> __device__ __forceinline__ static void noise(T* g, const T* u, const T* p, T) { g[0] = p[1] * u[0]; }
+};
+struct EmLinAdd1 {
+  static constexpr int N = 1, NP = 2, M = 1;
+  static constexpr bool kDiagonal = true;
+  template <class T> __device__ __forceinline__ static void rhs(T* f, const T* u, const T* p, T) { f[0] = p[0] * u[0]; }
+  template <class T> __device__ __forceinline__ static void noise(T* g, const T*, const T* p, T) { g[0] = p[1]; }
+};
+struct EmLinAdd2 {
+  static constexpr int N = 2, NP = 2, M = 2;
+  static constexpr bool kDiagonal = true;
+  template <class T> __device__ __forceinline__ static void rhs(T* f, const T* u, const T* p, T) {
+    f[0] = p[0] * u[0]; f[1] = p[0] * u[1];
+  }
+  template <class T> __device__ __forceinline__ static void noise(T* g, const T*, const T* p, T) { g[0] = p[1]; g[1] = p[1]; }
+};
+struct EmOU {
+  static constexpr int N = 1, NP = 3, M = 1;
+  static constexpr bool kDiagonal = true;
+  template <class T> __device__ __forceinline__ static void rhs(T* f, const T* u, const T* p, T) { f[0] = p[0] * (p[1] - u[0]); }
+  template <class T> __device__ __forceinline__ static void noise(T* g, const T*, const T* p, T) { g[0] = p[2]; }
+};
+struct EmNonDiag2x4 {
+  static constexpr int N = 2, NP = 1, M = 4;
+  static constexpr bool kDiagonal = false;
+  template <class T> __device__ __forceinline__ static void rhs(T* f, const T* u, const T* p, T) {
+    f[0] = p[0] * u[0]; f[1] = p[0] * u[1];
+  }
+  template <class T> __device__ __forceinline__ static void noise(T* g, const T* u, const T*, T) {
+    g[0] = T(0.3) * u[0]; g[1] = T(0.6) * u[0]; g[2] = T(0.9) * u[0]; g[3] = T(0.12) * u[0];
+    g[4] = T(1.2) * u[1]; g[5] = T(0.2) * u[1]; g[6] = T(0.3) * u[1]; g[7] = T(1.8) * u[1];
+  }
+};
+
+}  // namespace sde

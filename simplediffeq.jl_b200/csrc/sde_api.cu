@@ -20,6 +20,7 @@
 #include "../../include/simplediffeq_cuda.h"
 #include "device/sde_common.cuh"
 #include "sde_builtin_decl.h"
+#include "sde_internal.h"
 #include "sde_interp_host_gen.h"
 
 // ids in the public header and in the device headers must agree
@@ -39,9 +40,7 @@ extern const char* const sde_embedded_names[];
 extern const char* const sde_embedded_sources[];
 extern const int sde_embedded_count;
 
-namespace {
-
-constexpr int kBlock = 128;
+namespace sde_host {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
@@ -56,12 +55,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define SDE_CUDA(call)                                                                      \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess)                                                                  \
-      return fail(SDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
+}  // namespace sde_host
+using namespace sde_host;
+
+namespace {
+
 
 bool is_adaptive(int alg) { return alg == SDE_ALG_ATSIT5 || alg == SDE_ALG_AVERN7 || alg == SDE_ALG_AVERN9; }
 
@@ -91,7 +89,6 @@ size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
   const int LS = (S * n_state) | 1;
   return (size_t)(block / 32) * 32 * LS * es;
 }
-size_t esize(int dtype) { return dtype == SDE_F64 ? 8 : 4; }
 
 struct Compiled {
   cudaLibrary_t lib = nullptr;
@@ -212,6 +209,8 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
   return s;
 }
 
+}  // namespace
+namespace sde_host {
 int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log) {
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, program.c_str(), "sde_user.cu", sde_embedded_count,
@@ -247,6 +246,8 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
   nvrtcDestroyProgram(&prog);
   return SDE_OK;
 }
+}  // namespace sde_host
+namespace {
 
 // returns the cache entry (compiled; module loaded only if `load`)
 int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
@@ -335,6 +336,8 @@ void build_save_plan(int alg, const T* tgrid, int64_t n_steps, T t0, T dt, const
 // host-buffer solve the pool is trimmed to SDE_POOL_KEEP_MB (default 4096 MB), and sde_trim()
 // returns everything.
 // --------------------------------------------------------------------------------------------
+}  // namespace
+namespace sde_host {
 std::mutex g_pool_mu;
 std::map<int, cudaMemPool_t> g_pools;
 
@@ -362,6 +365,8 @@ size_t pool_keep_bytes() {
   const long long mb = e ? atoll(e) : 4096;
   return (size_t)std::max<long long>(0, mb) << 20;
 }
+}  // namespace sde_host
+namespace {
 
 // --------------------------------------------------------------------------------------------
 // per-solve device constants (identical for every piece of a chunked solve): time grid, saveat

@@ -24,7 +24,7 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "tableau_named.hpp", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle_em.cpp", "tableau_named.hpp", "Makefile")]
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in src)):
         return LIB_PATH
@@ -113,3 +113,51 @@ def solve(system, alg, u0, p, t0, tf, dt, *, dtype=np.float64, abstol=1e-6, relt
     r = OracleResult()
     r.u, r.t, r.n, r.naccept, r.nreject, r.retcode = out_u, out_t, out_n, nacc, nrej, ret
     return r
+
+
+# ---- SimpleEM (oracle_em.cpp) ------------------------------------------------------------------
+EM_SYS = dict(gbm=0, linadd1=1, linadd2=2, ou=3, nondiag2x4=4)
+
+
+def em_dims(system):
+    L = lib()
+    a, b, c, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = L.oracle_em_dims(EM_SYS[system], ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d))
+    assert rc == 0
+    return a.value, b.value, c.value, bool(d.value)
+
+
+def em_solve(system, u0_soa, p_soa, t0, dt, n_steps, noise, n_threads=4):
+    """u0_soa [N][n], p_soa [NP][n], noise [n_steps][M][n] -> [n][n_steps+1][N] (every state)."""
+    L = lib()
+    dtype = u0_soa.dtype
+    N, n = u0_soa.shape
+    u0c, pc, zc = (np.ascontiguousarray(x, dtype=dtype) for x in (u0_soa, p_soa, noise))
+    out = np.empty((n, n_steps + 1, N), dtype=dtype)
+    L.oracle_em_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_int]
+    rc = L.oracle_em_solve(EM_SYS[system], 0 if dtype == np.float64 else 1, n, _ptr(u0c), _ptr(pc), float(t0),
+                           float(dt), int(n_steps), _ptr(zc), _ptr(out), n_threads)
+    assert rc == 0
+    return out
+
+
+def em_normals(dtype, seed, traj_offset, n_traj, n_steps, M):
+    """The normals of the CUDA path's noise specification (Philox4x32-10 + Box-Muller): [n_steps][M][n]."""
+    L = lib()
+    out = np.empty((n_steps, M, n_traj), dtype=dtype)
+    L.oracle_em_normals.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                    ctypes.c_int, ctypes.c_void_p]
+    L.oracle_em_normals(0 if np.dtype(dtype) == np.float64 else 1, seed, traj_offset, n_traj, n_steps, M, _ptr(out))
+    return out
+
+
+def philox4x32_10(ctr, key):
+    L = lib()
+    c = (ctypes.c_uint32 * 4)(*ctr)
+    k = (ctypes.c_uint32 * 2)(*key)
+    o = (ctypes.c_uint32 * 4)()
+    L.oracle_philox4x32_10.restype = None
+    L.oracle_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
