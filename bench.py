@@ -127,6 +127,30 @@ def cpu_oracle_rate(n_sample, n_threads, seconds_target=None):
     return n_sample * N_STEPS / dt, dt
 
 
+def config0_atsit5(S, oracle_lib, cores, dev):
+    """BASELINE.json configs[0] next to the headline: Lorenz 10 k rho-sweep, GPUSimpleATsit5,
+    abstol = reltol = 1e-8, tspan (0,10) -- the reference's CPU-runnable case ("GPUSimpleATsit5 under
+    EnsembleThreads"): the oracle on all host threads vs the GPU through the host-buffer C-ABI call,
+    in accepted trajectory-steps/s, with the step-count parity of the two."""
+    n = 10_000
+    u0, p = lorenz_inputs_np(0, n, n)
+    dt0 = float(np.float32(0.1))
+    t0 = time.perf_counter()
+    o = oracle_lib.solve("lorenz", "ATsit5", u0.T, p.T, 0.0, 10.0, dt0, abstol=1e-8, reltol=1e-8, n_threads=cores)
+    cpu_s = time.perf_counter() - t0
+    alg = S.GPUSimpleATsit5()
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g = S.solve_arrays(S.systems.lorenz, alg, u0, p, (0.0, 10.0), dt=dt0, abstol=1e-8, reltol=1e-8, devices=[dev.index or 0])
+        best = min(best, time.perf_counter() - t0)
+    acc = int(o.naccept.sum())
+    return {"workload": "Lorenz 10k rho-sweep, GPUSimpleATsit5 tol 1e-8, tspan (0,10), endpoint only",
+            "accepted_steps": acc, "cpu_steps_per_s": acc / cpu_s, "cpu_cores": cores, "cpu_kind": "port",
+            "gpu_e2e_steps_per_s": int(g["naccept"].sum()) / best, "gpu_e2e_ms": best * 1e3,
+            "identical_step_counts_frac": float(np.mean(g["naccept"] == o.naccept))}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; Julia unavailable) on all
     host threads, one bounded sample per step."""
@@ -309,6 +333,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d of 10M trajectories x 10000 steps in %.1f s, %d std::threads (C++ restatement of GPUSimpleTsit5; Julia unavailable)" % (n_s, secs, cores)}
             line["parity_spot_check"] = {"trajectories": 512, "bit_identical_to_oracle": same}
+            line["config0_atsit5"] = config0_atsit5(S, oracle_lib, cores, dev)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -51,6 +51,8 @@ alg_id(::GPUSimpleVern7) = Int32(3)
 alg_id(::GPUSimpleAVern7) = Int32(4)
 alg_id(::GPUSimpleVern9) = Int32(5)
 alg_id(::GPUSimpleAVern9) = Int32(6)
+alg_id(::GPUSimpleEuler) = Int32(7)
+const SavesEveryStep = Union{GPUSimpleRK4, GPUSimpleEuler}     # no saveat / save_everystep keywords in the reference
 is_adaptive(alg) = alg isa Union{GPUSimpleATsit5, GPUSimpleAVern7, GPUSimpleAVern9}
 
 "Ensemble algorithm selecting the B200 library; `devices` = CUDA ordinals to shard over."
@@ -96,9 +98,9 @@ register_device_rhs!(f, rhs::DeviceRHS) = (DEVICE_RHS[f] = rhs)
 
 # ---- the ensemble solve ---------------------------------------------------------------------------
 function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTsit5, GPUSimpleATsit5,
-            GPUSimpleRK4, GPUSimpleVern7, GPUSimpleAVern7, GPUSimpleVern9, GPUSimpleAVern9},
+            GPUSimpleRK4, GPUSimpleEuler, GPUSimpleVern7, GPUSimpleAVern7, GPUSimpleVern9, GPUSimpleAVern9},
         ensemblealg::EnsembleCUDAB200;
-        trajectories, dt = alg isa GPUSimpleRK4 ? error("dt is required for this algorithm") : 0.1f0,
+        trajectories, dt = alg isa SavesEveryStep ? error("dt is required for this algorithm") : 0.1f0,
         abstol = 1.0f-6, reltol = 1.0f-3, saveat = nothing, save_everystep = true,
         layout = SDE_LAYOUT_TRAJ_MAJOR, compat = 0, kwargs...)
     prob = ensembleprob.prob
@@ -123,37 +125,49 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTs
     t0, tf = T(prob.tspan[1]), T(prob.tspan[2])
     dtT = T(dt)
     adaptive = is_adaptive(alg)
-    save_mode = alg isa GPUSimpleRK4 ? SDE_SAVE_EVERYSTEP :
+    save_mode = alg isa SavesEveryStep ? SDE_SAVE_EVERYSTEP :
                 saveat !== nothing ? SDE_SAVE_SAVEAT :
                 save_everystep ? SDE_SAVE_EVERYSTEP : SDE_SAVE_ENDPOINT
-    adaptive && save_mode == SDE_SAVE_EVERYSTEP &&
-        error("adaptive save_everystep=true is not provided by the device path yet; pass saveat or save_everystep=false")
     tgrid = adaptive ? T[] : collect(T, t0:dtT:tf)          # _ts = tspan[1]:dt:tspan[2]
     sa = saveat === nothing ? T[] : collect(T, saveat)
     n_steps = adaptive ? 0 : length(tgrid) - 1
-    slots = save_mode == SDE_SAVE_SAVEAT ? length(sa) : save_mode == SDE_SAVE_EVERYSTEP ? n_steps + 1 : 1
-
-    out_u = save_mode == SDE_SAVE_ENDPOINT ? Matrix{T}(undef, n, N) : Array{T}(undef, N, slots, n)  # traj-major
-    out_t = Vector{T}(undef, n)
     nacc, nrej, ret = zeros(Int32, n), zeros(Int32, n), zeros(Int32, n)
-    GC.@preserve tgrid sa begin
-        opt = Ref(SdeOptions(alg_id(alg), T === Float64 ? 0 : 1, save_mode, layout, compat, 0, n,
-            t0, tf, dtT, T(abstol), T(reltol), n_steps,
-            isempty(tgrid) ? C_NULL : pointer(tgrid), isempty(sa) ? C_NULL : pointer(sa), length(sa), 0, 0))
-        check(ccall((:sde_solve, libsde), Cint,
-            (Ptr{Cvoid}, Ref{SdeOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32},
-                Ptr{Int32}, Ptr{Cint}, Cint),
-            rhs.handle, opt, u0, p, out_u, out_t, nacc, nrej, ret, ensemblealg.devices, length(ensemblealg.devices)))
-        any(==(1), ret) && error("dt<dtmin")            # what the reference throws (gpuatsit5.jl:256)
-        ts_fixed = T[]
-        if !adaptive
-            ts_fixed = Vector{T}(undef, max(slots, 2))
-            nw = Ref{Int64}(0)
-            check(ccall((:sde_fixed_times, libsde), Cint, (Ref{SdeOptions}, Ptr{Cvoid}, Int64, Ref{Int64}),
-                opt, ts_fixed, length(ts_fixed), nw))
-            resize!(ts_fixed, nw[])
+
+    function call(mode, capacity, out_u, out_t)
+        GC.@preserve tgrid sa begin
+            opt = Ref(SdeOptions(alg_id(alg), T === Float64 ? 0 : 1, mode, layout, compat, 0, n,
+                t0, tf, dtT, T(abstol), T(reltol), n_steps,
+                isempty(tgrid) ? C_NULL : pointer(tgrid), isempty(sa) ? C_NULL : pointer(sa), length(sa), 0, capacity))
+            check(ccall((:sde_solve, libsde), Cint,
+                (Ptr{Cvoid}, Ref{SdeOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32},
+                    Ptr{Int32}, Ptr{Cint}, Cint),
+                rhs.handle, opt, u0, p, out_u, out_t, nacc, nrej, ret, ensemblealg.devices, length(ensemblealg.devices)))
+            any(==(1), ret) && error("dt<dtmin")            # what the reference throws (gpuatsit5.jl:256)
+            ts_fixed = T[]
+            if !adaptive
+                ts_fixed = Vector{T}(undef, max(n_steps + 1, length(sa), 2))
+                nw = Ref{Int64}(0)
+                check(ccall((:sde_fixed_times, libsde), Cint, (Ref{SdeOptions}, Ptr{Cvoid}, Int64, Ref{Int64}),
+                    opt, ts_fixed, length(ts_fixed), nw))
+                resize!(ts_fixed, nw[])
+            end
+            return ts_fixed
         end
     end
+
+    # adaptive save_everystep = true pushes every accepted step (gpuatsit5.jl:301-303): the step sequence is
+    # deterministic, so an endpoint-only pass gives the exact output sizes
+    capacity = 0
+    if adaptive && save_mode == SDE_SAVE_EVERYSTEP
+        call(SDE_SAVE_ENDPOINT, 0, Matrix{T}(undef, n, N), Vector{T}(undef, n))
+        capacity = Int(maximum(nacc)) + 1
+    end
+    slots = save_mode == SDE_SAVE_SAVEAT ? length(sa) :
+            save_mode == SDE_SAVE_EVERYSTEP ? (adaptive ? capacity : n_steps + 1) : 1
+    t_series = adaptive && save_mode == SDE_SAVE_EVERYSTEP
+    out_u = save_mode == SDE_SAVE_ENDPOINT ? Matrix{T}(undef, n, N) : Array{T}(undef, N, slots, n)  # traj-major
+    out_t = t_series ? Matrix{T}(undef, slots, n) : Vector{T}(undef, n)
+    ts_fixed = call(save_mode, capacity, out_u, out_t)
 
     SV = SVector{N, T}
     sols = map(1:n) do i
@@ -163,9 +177,93 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTs
             ts = adaptive ? T[t0, out_t[i]] : ts_fixed
         else
             us = collect(reinterpret(SV, vec(view(out_u, :, :, i))))
-            ts = save_mode == SDE_SAVE_SAVEAT ? sa : ts_fixed
+            ts = save_mode == SDE_SAVE_SAVEAT ? sa : t_series ? out_t[:, i] : ts_fixed
+            if t_series                      # naccept + 1 states were pushed
+                resize!(us, Int(nacc[i]) + 1); ts = ts[1:(Int(nacc[i]) + 1)]
+            end
         end
         build_solution(pi, alg, ts, us; calculate_error = false)   # retcode stays ReturnCode.Default
+    end
+    return EnsembleSolution(sols, 0.0, true)
+end
+
+# ==================================================================================================
+# SimpleEM: solve(EnsembleProblem(SDEProblem(f, g, u0, tspan, p); prob_func), SimpleEM(), EnsembleCUDAB200();
+#                 trajectories, dt, seed = 0)                 (replaces src/euler_maruyama.jl:48-94 per trajectory)
+# ==================================================================================================
+struct SdeEmOptions
+    dtype::Int32
+    save_mode::Int32
+    layout::Int32
+    noise_mode::Int32
+    n_traj::Int64
+    t0::Float64
+    dt::Float64
+    n_steps::Int64
+    seed::UInt64
+    traj_offset::Int64
+end
+
+"Device drift + diffusion: built-in SDE registry entry or CUDA-C source defining `rhs` and `noise`."
+struct DeviceSDE
+    handle::Ptr{Cvoid}
+    n_state::Int
+    n_param::Int
+    n_noise::Int
+end
+
+function builtin_sde(name::AbstractString)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sde_em_system_builtin, libsde), Cint, (Cstring, Ref{Ptr{Cvoid}}), name, h))
+    a, b, c, d = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    check(ccall((:sde_em_system_dims, libsde), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}), h[], a, b, c, d))
+    DeviceSDE(h[], a[], b[], c[])
+end
+
+function cuda_sde(src::AbstractString, n_state::Integer, n_param::Integer; n_noise::Integer = n_state, diagonal::Bool = true)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    log = Vector{UInt8}(undef, 16384)
+    rc = ccall((:sde_em_system_nvrtc, libsde), Cint,
+        (Cstring, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}, Ptr{UInt8}, Csize_t),
+        src, n_state, n_param, n_noise, diagonal ? 1 : 0, h, log, length(log))
+    rc == 0 || error("NVRTC: " * last_error())
+    DeviceSDE(h[], n_state, n_param, n_noise)
+end
+
+const DEVICE_SDE = IdDict{Any, DeviceSDE}()
+register_device_sde!(f, sde::DeviceSDE) = (DEVICE_SDE[f] = sde)
+
+function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::SimpleEM, ensemblealg::EnsembleCUDAB200;
+        trajectories, dt = error("dt required for SimpleEM"), seed::Integer = 0, kwargs...)
+    prob = ensembleprob.prob
+    @assert !SciMLBase.isinplace(prob)
+    T = eltype(prob.u0)
+    T in (Float64, Float32) || error("only Float64 / Float32 states run on the device")
+    f = prob.f isa SciMLBase.SDEFunction ? prob.f.f : prob.f
+    sde = get(DEVICE_SDE, f, nothing)
+    sde === nothing && error("no device SDE registered for this f (register_device_sde!)")
+    N, NP, n = sde.n_state, sde.n_param, Int(trajectories)
+    u0 = Matrix{T}(undef, n, N)
+    p = Matrix{T}(undef, n, NP)
+    for i in 1:n
+        pi = ensembleprob.prob_func(prob, i, 1)
+        pi.tspan == prob.tspan || error("prob_func may only change u0 and p on the device path")
+        u0[i, :] .= pi.u0
+        NP > 0 && (p[i, :] .= pi.p)
+    end
+    t0, dtT = T(prob.tspan[1]), T(dt)
+    nst = Int((T(prob.tspan[2]) - t0) / dtT)                 # n - 1; InexactError as in the reference (:66)
+    out_u = Array{T}(undef, N, nst + 1, n)                    # trajectory major, every state (:67)
+    opt = Ref(SdeEmOptions(T === Float64 ? 0 : 1, SDE_SAVE_EVERYSTEP, SDE_LAYOUT_TRAJ_MAJOR, 0, n, t0, dtT, nst,
+        UInt64(seed), 0))
+    check(ccall((:sde_em_solve, libsde), Cint,
+        (Ptr{Cvoid}, Ref{SdeEmOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cint),
+        sde.handle, opt, u0, p, C_NULL, out_u, ensemblealg.devices, length(ensemblealg.devices)))
+    ts = [muladd(T(i), dtT, t0) for i in 0:nst]               # :68 under @muladd
+    sols = map(1:n) do i
+        pi = ensembleprob.prob_func(prob, i, 1)
+        us = prob.u0 isa Number ? vec(out_u[1, :, i]) : collect(reinterpret(SVector{N, T}, vec(view(out_u, :, :, i))))
+        build_solution(pi, alg, ts, us; calculate_error = false)
     end
     return EnsembleSolution(sols, 0.0, true)
 end

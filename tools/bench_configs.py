@@ -111,5 +111,36 @@ def main():
             torch.cuda.empty_cache()
 
 
+def em_configs():
+    """SimpleEM: Philox-driven Euler-Maruyama ensembles, device resident."""
+    for dtype, nm in ((torch.float64, "f64"), (torch.float32, "f32")):
+        n, steps = 1 << 22, 1000
+        u0 = torch.ones((1, n), dtype=dtype, device=DEV)
+        p = torch.empty((2, n), dtype=dtype, device=DEV); p[0] = 0.1; p[1] = 0.2
+        out = torch.empty_like(u0)
+        ms, _ = timed(lambda: S.solve_em_device(S.sde_systems.gbm, u0, p, 0.0, 1e-3, steps, seed=1, out=out, sync=False), reps=3)
+        emit(config="EM: GBM 4Mi paths x 1000 steps endpoint " + nm, ms=ms, steps_per_s=n * steps / ms * 1e3,
+             normals_per_s=n * steps / ms * 1e3)
+    n, steps = 1 << 20, 1000
+    u0 = torch.ones((2, n), dtype=torch.float64, device=DEV)
+    p = torch.full((1, n), 1.01, dtype=torch.float64, device=DEV)
+    out = torch.empty_like(u0)
+    ms, _ = timed(lambda: S.solve_em_device(S.sde_systems.nondiag2x4, u0, p, 0.0, 1e-3, steps, seed=1, out=out, sync=False), reps=3)
+    emit(config="EM: nondiag2x4 1Mi paths x 1000 steps endpoint f64", ms=ms, steps_per_s=n * steps / ms * 1e3,
+         normals_per_s=4 * n * steps / ms * 1e3)
+    # every state kept (the reference's behaviour): HBM write bound, SoA
+    n, steps = 1 << 22, 255
+    u0 = torch.ones((1, n), dtype=torch.float64, device=DEV)
+    p = torch.empty((2, n), dtype=torch.float64, device=DEV); p[0] = 0.1; p[1] = 0.2
+    out = torch.empty((steps + 1, 1, n), dtype=torch.float64, device=DEV)
+    ms, _ = timed(lambda: S.solve_em_device(S.sde_systems.gbm, u0, p, 0.0, 1 / 256, steps, seed=1, save_mode=2, layout=1, out=out, sync=False), reps=3)
+    gbs = n * (steps + 1) * 8 / ms / 1e6
+    emit(config="EM: GBM 4Mi paths x 255 steps every step SoA f64", ms=ms, steps_per_s=n * steps / ms * 1e3, hbm_gbs=gbs, hbm_frac=gbs / HBM)
+
+
 if __name__ == "__main__":
-    main()
+    if "--em" in sys.argv:
+        em_configs()
+    else:
+        main()
+        em_configs()
