@@ -162,3 +162,13 @@ def test_em_python_mirror_reference_tests(sde):
     assert len(es) == 7 and es[2].u[0, 0] == 1.5 and es[2].u.shape == (5, 1)
     again = sde.solve(ens, sde.SimpleEM(), dt=0.25, trajectories=7, seed=11)
     assert _bits(es.u_raw, again.u_raw)                                              # reproducible
+
+
+def test_em_committed_golden_vectors(sde):
+    """tests/golden/golden_em_v1.json (oracle outputs with their increments): the CUDA path reproduces them bit for bit."""
+    from test_oracle_em import _golden_em, golden_em_arrays
+    for case in _golden_em():
+        u0, p, z, want = golden_em_arrays(case)
+        got = sde.solve_em_arrays(getattr(sde.sde_systems, case["system"]), u0, p, case["t0"], case["dt"], case["n_steps"],
+                                  noise=z, layout=0)
+        assert _bits(got, want), (case["system"], case["dtype"])

@@ -120,3 +120,30 @@ def test_vector_diagonal_and_scalar_forms_agree_to_rounding():
     assert np.allclose(v[:, :, 0], s0[:, :, 0], rtol=1e-13, atol=1e-14)
     assert np.allclose(v[:, :, 1], s1[:, :, 0], rtol=1e-13, atol=1e-14)
     assert not np.array_equal(v[:, :, 0], s0[:, :, 0])      # but not the same rounding
+
+
+def _golden_em():
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_em_v1.json")
+    return json.load(open(path))["cases"]
+
+
+def _unhex(h, dtype, shape):
+    return np.frombuffer(bytes.fromhex("".join(h)), dtype=dtype).reshape(shape).copy()
+
+
+def golden_em_arrays(case):
+    T = np.dtype(case["dtype"])
+    N, NP, M, _ = O.em_dims(case["system"])
+    n, steps = case["n"], case["n_steps"]
+    return (_unhex(case["u0"], T, (N, n)), _unhex(case["p"], T, (NP, n)), _unhex(case["noise"], T, (steps, M, n)),
+            _unhex(case["out"], T, (n, steps + 1, N)))
+
+
+def test_oracle_em_reproduces_committed_golden_vectors():
+    cases = _golden_em()
+    assert len(cases) == 10
+    for case in cases:
+        u0, p, z, want = golden_em_arrays(case)
+        got = O.em_solve(case["system"], u0, p, case["t0"], case["dt"], case["n_steps"], z)
+        assert got.tobytes() == want.tobytes(), (case["system"], case["dtype"])

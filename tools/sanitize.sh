@@ -16,9 +16,19 @@ S.solve_arrays(S.systems.lorenz, S.GPUSimpleVern7(), u0s, ps, (0.0, 1.0), dt=0.0
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7)           # work queue
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleAVern9(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-9, reltol=1e-9, saveat=sa, save_mode=1, layout=1)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7, save_mode=2, out_capacity=64)
+# SimpleEM: Philox stream, provided noise, non-diagonal; then the double-buffered pieces of the host path
+import os
+z = np.random.default_rng(0).standard_normal((16, 4, n))
+S.solve_em_arrays(S.sde_systems.gbm, np.ones((1, n)), np.tile([[0.1], [0.2]], (1, n)), 0.0, 1 / 16, 16, seed=3)
+S.solve_em_arrays(S.sde_systems.nondiag2x4, np.ones((2, n)), np.full((1, n), 1.01), 0.0, 1 / 16, 16, noise=z, layout=1)
+S.em_noise(np.float32, 5, n, 9, 3)
+os.environ["SDE_TUNE_PIECE"] = "96"
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, saveat=sa, save_mode=1, layout=0)
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7, saveat=sa, save_mode=1, layout=1)
+S.solve_em_arrays(S.sde_systems.gbm, np.ones((1, n)), np.tile([[0.1], [0.2]], (1, n)), 0.0, 1 / 16, 16, seed=3)
 print("sanitize workload done")
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck initcheck racecheck synccheck; do
   echo "=== compute-sanitizer --tool $tool"
   timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/sde_sanitize.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize workload done|Error|error" | head -8
 done
