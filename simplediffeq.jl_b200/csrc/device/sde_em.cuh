@@ -9,7 +9,8 @@
 //   the normal with linear index q = step*M + m of global trajectory g is element q % K of Philox4x32-10
 //   block b = q / K (K = 2 for double, 4 for float), counter (g_lo, g_hi, b_lo, b_hi), key (seed_lo, seed_hi);
 //   double: a = r0 | r1<<32, c = r2 | r3<<32, u1 = ((a>>11)+1) 2^-53 in (0,1], u2 = (c>>11) 2^-53 in [0,1),
-//           rad = sqrt(-2 ln u1), z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2)          (Box-Muller)
+//           rad = sqrt(-2 ln u1), z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2)          (Box-Muller;
+//           ln and sin/cos are table-driven FP64 routines accurate to ~2e-16, see NormalBlock<double>)
 //   float : (r0,r1) and (r2,r3): u1 = ((r>>8)+1) 2^-24, u2 = (r'>>8) 2^-24, same transform
 // or (kNoiseProvided) from a caller-supplied array noise[(step*M + m) * noise_ld + traj], which is how
 // the parity tests feed the kernel and the CPU oracle the same increments.
@@ -61,23 +62,24 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
 template <class T> struct NormalBlock;
 template <> struct NormalBlock<double> {
   static constexpr int K = 2;
-  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, double* z) {
+  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, double* z, CtrlTab tab) {
     unsigned r[4];
     philox4x32_10((unsigned)traj, (unsigned)(traj >> 32), (unsigned)b, (unsigned)(b >> 32),
                   (unsigned)seed, (unsigned)(seed >> 32), r);
     const u64 a = (u64)r[0] | ((u64)r[1] << 32), c = (u64)r[2] | ((u64)r[3] << 32);
-    const double u1 = (double)((a >> 11) + 1ull) * 1.1102230246251565e-16;   // 2^-53, (0,1]
-    const double u2 = (double)(c >> 11) * 1.1102230246251565e-16;            // [0,1)
-    const double rad = sqrt(-2.0 * log(u1));
+    const double u1 = (double)((a >> 11) + 1ull) * 1.1102230246251565e-16;   // 2^-53: (0,1]
+    const double v = (double)(c >> 11) * 4.4408920985006262e-16;             // 2^-51: 4 u2 in [0,4)
+    // rad = sqrt(-2 ln u1), ln through the controller's table-driven log2 (|.|: log2(1) is +2e-18, not 0)
+    const double rad = sqrt(fabs(sde_log2_fast(u1, tab) * ctrl_const(tab, kC_neg2ln2)));
     double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
+    sde_sincos_halfpi(v, tab, &sn, &cs);      // angle 2 pi u2 = (pi/2) v
     z[0] = rad * cs;
     z[1] = rad * sn;
   }
 };
 template <> struct NormalBlock<float> {
   static constexpr int K = 4;
-  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, float* z) {
+  __device__ __forceinline__ static void make(u64 seed, u64 traj, u64 b, float* z, CtrlTab) {
     unsigned r[4];
     philox4x32_10((unsigned)traj, (unsigned)(traj >> 32), (unsigned)b, (unsigned)(b >> 32),
                   (unsigned)seed, (unsigned)(seed >> 32), r);
@@ -94,6 +96,14 @@ template <> struct NormalBlock<float> {
   }
 };
 
+// the generator's constants: one shared-memory copy of k_ctrl per CTA (all threads must call this)
+__device__ __forceinline__ CtrlTab em_load_table() {
+  __shared__ __align__(16) double s_tab[kC_count];
+  for (int i = threadIdx.x; i < kC_count; i += blockDim.x) s_tab[i] = k_ctrl[i];
+  __syncthreads();
+  return s_tab;
+}
+
 // sequential reader of one trajectory's normal stream (linear index q = step*M + m)
 template <class T, int NOISE>
 struct NoiseStream {
@@ -101,15 +111,16 @@ struct NoiseStream {
   const EMArgs<T>& a;
   i64 traj;      // local index
   i64 q;
+  CtrlTab tab;
   T z[K];
-  __device__ __forceinline__ NoiseStream(const EMArgs<T>& a_, i64 traj_) : a(a_), traj(traj_), q(0) {}
+  __device__ __forceinline__ NoiseStream(const EMArgs<T>& a_, i64 traj_, CtrlTab tab_) : a(a_), traj(traj_), q(0), tab(tab_) {}
   __device__ __forceinline__ T next() {
     T v;
     if (NOISE == kNoiseProvided) {
       v = a.noise[q * a.noise_ld + traj];
     } else {
       const int k = (int)(q % K);
-      if (k == 0) NormalBlock<T>::make(a.seed, (u64)(a.traj_offset + traj), (u64)(q / K), z);
+      if (k == 0) NormalBlock<T>::make(a.seed, (u64)(a.traj_offset + traj), (u64)(q / K), z, tab);
       v = z[0];
 #pragma unroll
       for (int j = 1; j < K; ++j) if (k == j) v = z[j];
@@ -136,6 +147,8 @@ template <class Sys, class T, int SAVE, int NOISE>
 __device__ __forceinline__ void em_body(const EMArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP, M = Sys::M;
   constexpr bool kDiag = Sys::kDiagonal;
+  CtrlTab tab = nullptr;
+  if (NOISE == kNoisePhilox && sizeof(T) == 8) tab = em_load_table();
   const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (traj >= a.n_traj) return;
   T u[N], p[NP > 0 ? NP : 1];
@@ -145,7 +158,7 @@ __device__ __forceinline__ void em_body(const EMArgs<T>& a) {
   for (int c = 0; c < NP; ++c) p[c] = a.p[(i64)c * a.ld_in + traj];
   const T dt = a.dt;
   const T sqdt = sde_sqrt(dt);
-  NoiseStream<T, NOISE> ns(a, traj);
+  NoiseStream<T, NOISE> ns(a, traj, tab);
   if (SAVE == kSaveEveryStep) em_put<T, N>(a, traj, 0, u);
   for (i64 s = 0; s < a.n_steps; ++s) {
     const T tprev = fma((T)s, dt, a.t0);
@@ -187,11 +200,13 @@ __device__ __forceinline__ void em_body(const EMArgs<T>& a) {
 template <class T>
 __device__ __forceinline__ void em_noise_body(u64 seed, i64 traj_offset, i64 n_traj, i64 n_normals, T* out, i64 ld) {
   constexpr int K = NormalBlock<T>::K;
+  CtrlTab tab = nullptr;
+  if (sizeof(T) == 8) tab = em_load_table();
   const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (traj >= n_traj) return;
   T z[K];
   for (i64 b = 0; b * K < n_normals; ++b) {
-    NormalBlock<T>::make(seed, (u64)(traj_offset + traj), (u64)b, z);
+    NormalBlock<T>::make(seed, (u64)(traj_offset + traj), (u64)b, z, tab);
 #pragma unroll
     for (int j = 0; j < K; ++j)
       if (b * K + j < n_normals) out[(b * K + j) * ld + traj] = z[j];

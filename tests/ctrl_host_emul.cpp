@@ -27,6 +27,9 @@ double emul_max_abs_nan2(double a, double b) { return sde::max_abs_nan2(a, b); }
 double emul_min_abs_nan1(double a, double b) { return sde::min_abs_nan1(a, b); }
 double emul_jl_max(double a, double b) { return sde::jl_max(a, b); }
 double emul_jl_min(double a, double b) { return sde::jl_min(a, b); }
+void emul_sincos_halfpi(const double* v, double* sn, double* cs, long n) {
+  for (long i = 0; i < n; ++i) sde::sde_sincos_halfpi(v[i], sde::k_ctrl, &sn[i], &cs[i]);
+}
 int emul_ctrl_count() { return sde::kC_count; }
 double emul_ctrl(int i) { return sde::k_ctrl[i]; }
 }

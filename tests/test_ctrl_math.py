@@ -75,6 +75,22 @@ def test_exp2_fast_accuracy(emul):
     assert _apply(emul.emul_exp2, np.array([0.0, 1.0, -2.0])).tolist() == [1.0, 2.0, 0.25]
 
 
+def test_sincos_halfpi_accuracy(emul):
+    """sin/cos((pi/2) v), v in [0,4): the angle function of the SimpleEM normal generator (sde_em.cuh)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(9)
+    v = np.concatenate([rng.uniform(0, 4, 4000), np.arange(0, 4, 0.5), np.arange(0, 4, 0.5) + 2.0 ** -51,
+                        [np.nextafter(4.0, 0.0), 0.5 - 2.0 ** -53, 1.5, 2.5, 3.5]])
+    sn, cs = np.empty_like(v), np.empty_like(v)
+    emul.emul_sincos_halfpi(v.ctypes.data_as(ctypes.c_void_p), sn.ctypes.data_as(ctypes.c_void_p),
+                            cs.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(v)))
+    es = max(float(abs(mp.sin(mp.pi / 2 * mp.mpf(float(x))) - mp.mpf(float(s)))) for x, s in zip(v, sn))
+    ec = max(float(abs(mp.cos(mp.pi / 2 * mp.mpf(float(x))) - mp.mpf(float(c)))) for x, c in zip(v, cs))
+    assert es < 2.3e-16 and ec < 2.3e-16, (es, ec)
+    assert np.max(np.abs(sn * sn + cs * cs - 1)) < 5e-16
+
+
 def test_rcp_fast_accuracy(emul):
     rng = np.random.default_rng(3)
     x = 10.0 ** rng.uniform(-12, 6, 5000)
