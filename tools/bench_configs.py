@@ -138,8 +138,28 @@ def em_configs():
     emit(config="EM: GBM 4Mi paths x 255 steps every step SoA f64", ms=ms, steps_per_s=n * steps / ms * 1e3, hbm_gbs=gbs, hbm_frac=gbs / HBM)
 
 
+def adaptive_saveat_configs():
+    """Adaptive + saveat (dense output at 101 points): the output side of the persistent work-queue kernels."""
+    n = 1 << 20
+    saveat = S.jl_range(0.0, 0.1, 10.0)
+    for shuffled in (False, True):
+        u0, p = lorenz(n)
+        if shuffled:
+            perm = (torch.arange(n, dtype=torch.int64, device=DEV) * 2654435761) % n
+            p = p[:, perm].contiguous()
+        for layout, nm in ((1, "soa"), (0, "traj_major")):
+            out = torch.empty((n, 101, 3) if layout == 0 else (101, 3, n), dtype=torch.float64, device=DEV)
+            ms, r = timed(lambda: S.solve_device(S.systems.lorenz, S.GPUSimpleATsit5(), u0, p, (0.0, 10.0), dt=DT0, abstol=1e-8,
+                                                 reltol=1e-8, saveat=saveat, save_mode=1, layout=layout, out=out, sync=False), reps=3)
+            acc = int(r["naccept"].sum().item())
+            emit(config="ATsit5 Lorenz 1Mi tol 1e-8 saveat=0:0.1:10 %s %s" % ("shuffled" if shuffled else "sorted", nm), ms=ms,
+                 accepted_steps_per_s=acc / ms * 1e3, out_gbs=n * 101 * 24 / ms / 1e6)
+
+
 if __name__ == "__main__":
-    if "--em" in sys.argv:
+    if "--adaptive-saveat" in sys.argv:
+        adaptive_saveat_configs()
+    elif "--em" in sys.argv:
         em_configs()
     else:
         main()
