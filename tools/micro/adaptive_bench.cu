@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) kern(const __grid_constant__ sde:
   sde::adaptive_body<Sys, double, sde::METHOD<Sys, double>, sde::kSaveEndpoint, V9, false>(a);
 }
 int main(int argc, char** argv) {
-  const long long n = 1 << 20;
+  const long long n = 1LL << (argc > 3 ? atoi(argv[3]) : 20);
   const int N = Sys::N, NP = Sys::NP;
   std::vector<double> u0((size_t)N * n, 0.0), p((size_t)NP * n);
   double tf = 10.0, tol = argc > 1 ? atof(argv[1]) : 1e-8;
@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
   }
   std::vector<int> hna(n), hnr(n); cudaMemcpy(hna.data(), na, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hnr.data(), nr, n * 4, cudaMemcpyDeviceToHost);
   double acc = 0, rej = 0; for (long long i = 0; i < n; ++i) { acc += hna[i]; rej += hnr[i]; }
-  printf("%s regs=%d blocks/SM=%d block=%d: %.3f ms  attempts/s=%.4g (acc %.0f rej %.0f) %s\n", argv[0], fa.numRegs, per_sm, BLOCK, best,
+  printf("%s n=%lld regs=%d blocks/SM=%d block=%d: %.3f ms  attempts/s=%.4g (acc %.0f rej %.0f) %s\n", argv[0], n, fa.numRegs, per_sm, BLOCK, best,
          (acc + rej) / best * 1e3, acc, rej, cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
