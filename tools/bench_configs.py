@@ -156,8 +156,30 @@ def adaptive_saveat_configs():
                  accepted_steps_per_s=acc / ms * 1e3, out_gbs=n * 101 * 24 / ms / 1e6)
 
 
+def other_system_configs():
+    """The other registry entries (no BASELINE config): throughput with register pressure at N = 12 (N-body-lite)
+    and the stiff-ish Robertson rates; random inputs of tests/common.py."""
+    import common as C
+    n = 1 << 20
+    for name, span, dt, tol in (("nbody", (0.0, 1.0), 1e-3, 1e-8), ("robertson", (0.0, 1.0), 1e-3, 1e-8), ("vanderpol", (0.0, 1.0), 1e-3, 1e-8)):
+        sysm = getattr(S.systems, name)
+        u0n, pn = C.random_problem(name, n, np.float64, 5)
+        u0 = torch.from_numpy(np.ascontiguousarray(u0n.T)).to(DEV); p = torch.from_numpy(np.ascontiguousarray(pn.T)).to(DEV)
+        for alg in (S.GPUSimpleTsit5(), S.GPUSimpleVern9()):
+            ms, _ = timed(lambda: S.solve_device(sysm, alg, u0, p, span, dt=dt, stats=False, sync=False), reps=3)
+            emit(config="fixed %s %s 1Mi x 1000 steps f64" % (name, type(alg).__name__), ms=ms, steps_per_s=n * 1000 / ms * 1e3)
+        for alg in (S.GPUSimpleATsit5(), S.GPUSimpleAVern9()):
+            ms, r = timed(lambda: S.solve_device(sysm, alg, u0, p, span, dt=DT0, abstol=tol, reltol=tol, sync=False), reps=3)
+            acc = int(r["naccept"].sum().item()); rej = int(r["nreject"].sum().item())
+            emit(config="adaptive %s %s 1Mi tol %g f64" % (name, type(alg).__name__, tol), ms=ms, accepted_steps_per_s=acc / ms * 1e3,
+                 attempts_per_s=(acc + rej) / ms * 1e3, naccept_mean=acc / n, naccept_max=int(r["naccept"].max().item()),
+                 failed=int((r["retcode"] != 0).sum().item()))
+
+
 if __name__ == "__main__":
-    if "--adaptive-saveat" in sys.argv:
+    if "--others" in sys.argv:
+        other_system_configs()
+    elif "--adaptive-saveat" in sys.argv:
         adaptive_saveat_configs()
     elif "--em" in sys.argv:
         em_configs()
