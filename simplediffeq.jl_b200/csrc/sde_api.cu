@@ -779,6 +779,7 @@ int sde_solve_device(sde_system_t sys, const sde_options_t* opt, const void* d_u
                      int32_t* d_nreject, int32_t* d_retcode, void* stream, int async) {
   int rc = validate(sys, opt);
   if (rc != SDE_OK) return rc;
+  if (opt->n_traj == 0) return SDE_OK;
   if (!d_u0 || !d_out_u || (sys->n_param > 0 && !d_p)) return fail(SDE_ERR_INVALID, "null device buffer");
   if (ld_in < opt->n_traj || ld_out < opt->n_traj) return fail(SDE_ERR_INVALID, "ld_in / ld_out smaller than n_traj");
   cudaStream_t st = (cudaStream_t)stream;
@@ -793,9 +794,9 @@ int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const 
               int n_dev) {
   int rc = validate(sys, opt);
   if (rc != SDE_OK) return rc;
-  if (!u0 || !out_u || (sys->n_param > 0 && !p)) return fail(SDE_ERR_INVALID, "null host buffer");
   if (n_dev < 0 || (n_dev > 0 && !devices)) return fail(SDE_ERR_INVALID, "bad device list");
-  if (opt->n_traj == 0) return SDE_OK;
+  if (opt->n_traj == 0) return SDE_OK;      // an empty ensemble: nothing to read or write
+  if (!u0 || !out_u || (sys->n_param > 0 && !p)) return fail(SDE_ERR_INVALID, "null host buffer");
   if (n_dev <= 1) {
     RangeSource all;
     all.lo = 0; all.hi = opt->n_traj;

@@ -360,6 +360,7 @@ int sde_em_solve_device(sde_em_system_t sys, const sde_em_options_t* opt, const 
                         const void* d_noise, int64_t noise_ld, void* d_out_u, int64_t ld_out, void* stream, int async) {
   int rc = em_validate(sys, opt);
   if (rc != SDE_OK) return rc;
+  if (opt->n_traj == 0) return SDE_OK;
   if (!d_u0 || !d_out_u || (sys->n_param > 0 && !d_p)) return fail(SDE_ERR_INVALID, "null device buffer");
   if (ld_in < opt->n_traj || ld_out < opt->n_traj) return fail(SDE_ERR_INVALID, "ld_in / ld_out smaller than n_traj");
   if (opt->noise_mode == SDE_NOISE_PROVIDED && noise_ld < opt->n_traj) return fail(SDE_ERR_INVALID, "noise_ld smaller than n_traj");
@@ -377,11 +378,11 @@ int sde_em_solve(sde_em_system_t sys, const sde_em_options_t* opt, const void* u
                  void* out_u, const int* devices, int n_dev) {
   int rc = em_validate(sys, opt);
   if (rc != SDE_OK) return rc;
+  if (n_dev < 0 || (n_dev > 0 && !devices)) return fail(SDE_ERR_INVALID, "bad device list");
+  if (opt->n_traj == 0) return SDE_OK;
   if (!u0 || !out_u || (sys->n_param > 0 && !p)) return fail(SDE_ERR_INVALID, "null host buffer");
   if (opt->noise_mode == SDE_NOISE_PROVIDED && !noise && opt->n_steps > 0)
     return fail(SDE_ERR_INVALID, "noise_mode SDE_NOISE_PROVIDED needs a noise array");
-  if (n_dev < 0 || (n_dev > 0 && !devices)) return fail(SDE_ERR_INVALID, "bad device list");
-  if (opt->n_traj == 0) return SDE_OK;
   if (n_dev <= 1)
     return em_solve_shard(sys, opt, n_dev == 1 ? devices[0] : -1, 0, opt->n_traj, (const char*)u0, (const char*)p,
                           (const char*)noise, (char*)out_u, nullptr);
