@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 #include <chrono>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -211,19 +213,86 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
 
 }  // namespace
 namespace sde_host {
+
+// ---- on-disk cubin cache (keyed by a hash of everything that determines the cubin) -----------------
+// SDE_CACHE_DIR = directory (unset, empty or "off": no disk cache -- the library never writes outside a
+// directory it was given).  Makes a user RHS cost one NVRTC compile per (source, algorithm, dtype, save
+// mode) per machine instead of per process.
+static std::string cache_dir() {
+  const char* e = getenv("SDE_CACHE_DIR");
+  return (!e || !*e || !strcmp(e, "off")) ? std::string() : std::string(e);
+}
+static void fnv(unsigned long long* h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { *h ^= p[i]; *h *= 1099511628211ULL; }
+}
+static std::string cache_key(const std::string& program, const char* const* opts, int n_opts) {
+  unsigned long long a = 14695981039346656037ULL, b = 0x9E3779B97F4A7C15ULL;
+  auto mix = [&](const void* d, size_t n) { fnv(&a, d, n); fnv(&b, d, n); b = (b << 13) | (b >> 51); };
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  const int ver[3] = {SDE_VERSION, major, minor};
+  mix(ver, sizeof ver);
+  mix(program.data(), program.size());
+  for (int i = 0; i < n_opts; ++i) mix(opts[i], strlen(opts[i]) + 1);
+  for (int i = 0; i < sde_embedded_count; ++i) mix(sde_embedded_sources[i], strlen(sde_embedded_sources[i]) + 1);
+  char buf[40];
+  snprintf(buf, sizeof buf, "%016llx%016llx", a, b);
+  return buf;
+}
+static bool cache_load(const std::string& path, std::vector<char>* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) { out->resize((size_t)n); ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n; }
+  fclose(f);
+  if (!ok) out->clear();
+  return ok;
+}
+static void cache_store(const std::string& dir, const std::string& path, const std::vector<char>& data) {
+  std::string cmd_dir = dir;
+  for (size_t i = 1; i <= cmd_dir.size(); ++i)           // mkdir -p
+    if (i == cmd_dir.size() || cmd_dir[i] == '/') { std::string sub = cmd_dir.substr(0, i); mkdir(sub.c_str(), 0755); }
+  char tmp[64];
+  snprintf(tmp, sizeof tmp, ".tmp.%ld.%p", (long)getpid(), (const void*)&data);
+  const std::string t = dir + "/" + tmp;
+  FILE* f = fopen(t.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (!ok || rename(t.c_str(), path.c_str()) != 0) remove(t.c_str());   // atomic publish
+}
+
 int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log) {
+  const bool trace = getenv("SDE_TRACE") != nullptr;
+  char tune_k[96], tune32_k[96];
+  {
+    const int te = tune_stage_elems();
+    snprintf(tune_k, sizeof tune_k, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 45);
+    snprintf(tune32_k, sizeof tune32_k, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 93);
+  }
+  const char* key_opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
+  std::string dir, path;
+  if (cubin) {
+    dir = cache_dir();
+    if (!dir.empty()) {
+      path = dir + "/" + cache_key(program, key_opts, 7) + ".cubin";
+      if (cache_load(path, cubin)) {
+        if (trace) fprintf(stderr, "[sde trace] nvrtc: cache hit %s\n", path.c_str());
+        if (log) log->clear();
+        return SDE_OK;
+      }
+    }
+  }
+  const auto t_begin = std::chrono::steady_clock::now();
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, program.c_str(), "sde_user.cu", sde_embedded_count,
                                      sde_embedded_sources, sde_embedded_names);
   if (r != NVRTC_SUCCESS) return fail(SDE_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
-  char tune[96];
-  const int te = tune_stage_elems();
-  snprintf(tune, sizeof tune, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 45);
-  char tune32[96];
-  snprintf(tune32, sizeof tune32, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 93);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo",
-                        "-default-device", tune, tune32};
-  r = nvrtcCompileProgram(prog, 7, opts);
+  r = nvrtcCompileProgram(prog, 7, key_opts);
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
   std::string lg(ls, '\0');
@@ -242,6 +311,11 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
     }
     cubin->resize(cs);
     nvrtcGetCUBIN(prog, cubin->data());
+    if (!path.empty()) cache_store(dir, path, *cubin);
+    if (trace)
+      fprintf(stderr, "[sde trace] nvrtc: compiled %zu bytes in %.0f ms%s\n", cs,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(),
+              path.empty() ? "" : " (cached)");
   }
   nvrtcDestroyProgram(&prog);
   return SDE_OK;

@@ -171,6 +171,32 @@ def test_nvrtc_user_rhs_compiles_for_sm100a(sde):
         assert L.sde_system_prepare(user._handle, ctypes.byref(o)) == 0, L.sde_last_error()
 
 
+def test_nvrtc_cubin_disk_cache(sde, tmp_path, monkeypatch, capfd):
+    """SDE_CACHE_DIR: a user RHS is compiled once per (source, variant) per machine; a second handle with the
+    same source loads the cubin from disk (reported under SDE_TRACE), a different source does not."""
+    from simplediffeq_b200 import _lib
+    L = _lib.lib()
+    monkeypatch.setenv("SDE_CACHE_DIR", str(tmp_path / "cache"))
+    monkeypatch.setenv("SDE_TRACE", "1")
+
+    def prepare(src):
+        user = sde.CudaRHS(src, 3, 3)
+        keep = []
+        o = sde.api.make_options(sde.GPUSimpleTsit5(), np.dtype(np.float64), 4, (0.0, 1.0), 0.1, 1e-6, 1e-3, None, 0, 0, 0, 0, keep)
+        assert L.sde_system_prepare(user._handle, ctypes.byref(o)) == 0, L.sde_last_error()
+        return capfd.readouterr().err
+
+    first = prepare(LORENZ_SRC)
+    files = sorted((tmp_path / "cache").glob("*.cubin"))
+    assert "compiled" in first and "cache hit" not in first and len(files) == 1 and files[0].stat().st_size > 1000
+    second = prepare(LORENZ_SRC)
+    assert "cache hit" in second and "compiled" not in second
+    third = prepare(LORENZ_SRC.replace("p[2] * u[2]", "p[2] * u[2] * 1"))
+    assert "compiled" in third and len(list((tmp_path / "cache").glob("*.cubin"))) == 2
+    monkeypatch.setenv("SDE_CACHE_DIR", "off")
+    assert "cache hit" not in prepare(LORENZ_SRC)
+
+
 def test_nvrtc_compile_error_is_reported(sde):
     from simplediffeq_b200 import _lib
     with pytest.raises(_lib.SdeError) as e:
