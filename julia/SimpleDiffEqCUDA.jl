@@ -96,6 +96,19 @@ end
 const DEVICE_RHS = IdDict{Any, DeviceRHS}()
 register_device_rhs!(f, rhs::DeviceRHS) = (DEVICE_RHS[f] = rhs)
 
+# ---- zero-copy views of series outputs ------------------------------------------------------------
+# SDE_LAYOUT_SOA (out[i, c, slot] in column-major Julia = out_u[slot][c][i] in C) is the layout that
+# reaches 90 % of HBM bandwidth (DESIGN.md section 3); this wrapper presents trajectory i of such an
+# array as the `Vector{SVector{N,T}}`-like object `sol.u` is expected to be, without copying.
+struct SoASeries{N, T} <: AbstractVector{SVector{N, T}}
+    data::Array{T, 3}        # (n_traj, N, n_slots)
+    i::Int
+    len::Int
+end
+Base.size(s::SoASeries) = (s.len,)
+Base.@propagate_inbounds Base.getindex(s::SoASeries{N, T}, j::Int) where {N, T} =
+    SVector{N, T}(ntuple(c -> s.data[s.i, c, j], N))
+
 # ---- the ensemble solve ---------------------------------------------------------------------------
 function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTsit5, GPUSimpleATsit5,
             GPUSimpleRK4, GPUSimpleEuler, GPUSimpleVern7, GPUSimpleAVern7, GPUSimpleVern9, GPUSimpleAVern9},
@@ -165,8 +178,10 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTs
     slots = save_mode == SDE_SAVE_SAVEAT ? length(sa) :
             save_mode == SDE_SAVE_EVERYSTEP ? (adaptive ? capacity : n_steps + 1) : 1
     t_series = adaptive && save_mode == SDE_SAVE_EVERYSTEP
-    out_u = save_mode == SDE_SAVE_ENDPOINT ? Matrix{T}(undef, n, N) : Array{T}(undef, N, slots, n)  # traj-major
-    out_t = t_series ? Matrix{T}(undef, slots, n) : Vector{T}(undef, n)
+    soa = layout == SDE_LAYOUT_SOA
+    out_u = save_mode == SDE_SAVE_ENDPOINT ? Matrix{T}(undef, n, N) :
+            soa ? Array{T}(undef, n, N, slots) : Array{T}(undef, N, slots, n)
+    out_t = t_series ? (soa ? Matrix{T}(undef, n, slots) : Matrix{T}(undef, slots, n)) : Vector{T}(undef, n)
     ts_fixed = call(save_mode, capacity, out_u, out_t)
 
     SV = SVector{N, T}
@@ -176,11 +191,9 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::Union{GPUSimpleTs
             us = [SV(pi.u0), SV(ntuple(c -> out_u[i, c], N))]
             ts = adaptive ? T[t0, out_t[i]] : ts_fixed
         else
-            us = collect(reinterpret(SV, vec(view(out_u, :, :, i))))
-            ts = save_mode == SDE_SAVE_SAVEAT ? sa : t_series ? out_t[:, i] : ts_fixed
-            if t_series                      # naccept + 1 states were pushed
-                resize!(us, Int(nacc[i]) + 1); ts = ts[1:(Int(nacc[i]) + 1)]
-            end
+            len = t_series ? Int(nacc[i]) + 1 : slots      # adaptive every-step: naccept + 1 states were pushed
+            us = soa ? SoASeries{N, T}(out_u, i, len) : collect(reinterpret(SV, vec(view(out_u, :, :, i))))[1:len]
+            ts = save_mode == SDE_SAVE_SAVEAT ? sa : t_series ? (soa ? out_t[i, 1:len] : out_t[1:len, i]) : ts_fixed
         end
         build_solution(pi, alg, ts, us; calculate_error = false)   # retcode stays ReturnCode.Default
     end
