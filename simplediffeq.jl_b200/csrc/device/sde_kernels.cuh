@@ -324,51 +324,51 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
     // ---- work queue: idle lanes fetch the next trajectory (one atomic per warp per refill).
     // Fast path while every lane is busy: one vote.
     if (__any_sync(FULL, !active)) {
-    const unsigned want = __ballot_sync(FULL, !active && !drained);
-    if (want) {
-      const int leader = __ffs(want) - 1;
-      u64 base = 0;
-      if ((int)lane == leader) base = atomicAdd(a.queue, (u64)__popc(want));
-      base = __shfl_sync(FULL, base, leader);
-      if (!active && !drained) {
-        traj = (i64)base + __popc(want & ((1u << lane) - 1u));
-        if (traj < a.n_traj) {
-          load_problem<T, N, NP>(a, traj, u, p);
-          t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
-          lqold = lqold0;
-          cur = 0; nacc = 0; nrej = 0;
-          m.seed(u, p, t);
-#pragma unroll
-          for (int c = 0; c < N; ++c) uprev[c] = u[c];
-          m.begin_step();
-          if (SAVE == kSaveAt) {
-            if (a.n_save > 0 && a.t0 == a.saveat[0]) {
-              put_series<T, N>(a, traj, 0, u);
-              cur = 1;
+      const unsigned want = __ballot_sync(FULL, !active && !drained);
+      if (want) {
+        const int leader = __ffs(want) - 1;
+        u64 base = 0;
+        if ((int)lane == leader) base = atomicAdd(a.queue, (u64)__popc(want));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active && !drained) {
+          traj = (i64)base + __popc(want & ((1u << lane) - 1u));
+          if (traj < a.n_traj) {
+            load_problem<T, N, NP>(a, traj, u, p);
+            t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
+            lqold = lqold0;
+            cur = 0; nacc = 0; nrej = 0;
+            m.seed(u, p, t);
+  #pragma unroll
+            for (int c = 0; c < N; ++c) uprev[c] = u[c];
+            m.begin_step();
+            if (SAVE == kSaveAt) {
+              if (a.n_save > 0 && a.t0 == a.saveat[0]) {
+                put_series<T, N>(a, traj, 0, u);
+                cur = 1;
+              }
             }
+            if (SAVE == kSaveEveryStep) {   // us = [u0], ts = [t0]   (gpuatsit5.jl:220-224)
+              put_series<T, N>(a, traj, 0, u);
+              put_series_time<T>(a, traj, 0, t);
+            }
+            active = true;
+            if (!(t < tf)) {   // `while t < tspan[2]` never entered
+              if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
+              if (SAVE != kSaveEveryStep && a.out_t) a.out_t[traj] = t;
+              if (a.naccept) a.naccept[traj] = 0;
+              if (a.nreject) a.nreject[traj] = 0;
+              if (a.retcode) a.retcode[traj] = kRetDefault;
+              active = false;
+            }
+          } else {
+            drained = true;
           }
-          if (SAVE == kSaveEveryStep) {   // us = [u0], ts = [t0]   (gpuatsit5.jl:220-224)
-            put_series<T, N>(a, traj, 0, u);
-            put_series_time<T>(a, traj, 0, t);
-          }
-          active = true;
-          if (!(t < tf)) {   // `while t < tspan[2]` never entered
-            if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
-            if (SAVE != kSaveEveryStep && a.out_t) a.out_t[traj] = t;
-            if (a.naccept) a.naccept[traj] = 0;
-            if (a.nreject) a.nreject[traj] = 0;
-            if (a.retcode) a.retcode[traj] = kRetDefault;
-            active = false;
-          }
-        } else {
-          drained = true;
         }
       }
-    }
-    if (__all_sync(FULL, !active)) {
-      if (__all_sync(FULL, drained)) break;   // warp-vote exit: nothing left anywhere
-      continue;
-    }
+      if (__all_sync(FULL, !active)) {
+        if (__all_sync(FULL, drained)) break;   // warp-vote exit: nothing left anywhere
+        continue;
+      }
     }
 
     if (active) {
