@@ -659,18 +659,26 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSour
     rc = device_pool(dev, &pool);
     if (rc != SDE_OK) return rc;
 
-    // piece size: a quarter of the range (at least 2^17 trajectories), bounded by the memory budget
+    // piece size: a quarter of the range (at least 2^17 trajectories, 2^21 for adaptive kernels), bounded by the memory budget
     // (60 % of what is free now plus what the pool already holds, shared by the kBuf buffer sets)
-    size_t free_b = 0, total_b = 0;
-    SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    unsigned long long pooled = 0, pool_used = 0;   // idle bytes the pool already holds count as free
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &pooled);
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &pool_used);
-    pooled = pooled > pool_used ? pooled - pool_used : 0;
     const size_t per_traj = es * ((size_t)N + NP + (size_t)N * slots + (t_series ? slots : 1)) + 12;
-    int64_t piece = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)(free_b + pooled)) / per_traj / kBuf);
     const int64_t range = src.max_piece();
-    int64_t want = std::max<int64_t>((range + 3) / 4, (int64_t)1 << 17);
+    unsigned long long pooled = 0;
+    int64_t piece = range;
+    if ((double)per_traj * (double)range * kBuf > 512.0 * 1048576.0) {
+      // large solves: bound the pieces by what is free now plus the idle bytes the pool already holds
+      // (cudaMemGetInfo costs ~0.3 ms, so small solves skip it: any B200 has 512 MB to spare)
+      size_t free_b = 0, total_b = 0;
+      SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      unsigned long long pool_used = 0;
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &pooled);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &pool_used);
+      pooled = pooled > pool_used ? pooled - pool_used : 0;
+      piece = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)(free_b + pooled)) / per_traj / kBuf);
+    }
+    // adaptive kernels are persistent (~1.5e5 lanes in flight) and end with a latency-bound tail of the
+    // longest trajectories, so their pieces must hold many trajectories per lane to stay efficient
+    int64_t want = std::max<int64_t>((range + 3) / 4, (int64_t)1 << (adaptive ? 21 : 17));
     if (const char* e = getenv("SDE_TUNE_PIECE")) want = std::max<int64_t>(32, atoll(e));   // measurement only
     piece = std::min<int64_t>(piece, std::min<int64_t>(want, range));
     if (piece > 32) piece = (piece + 31) & ~(int64_t)31;
@@ -888,8 +896,8 @@ int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const 
     if (is_adaptive(opt->alg) && !getenv("SDE_TUNE_STATIC_SHARDS")) {   // env knob: measurement only
       src.shared = &cursor;
       src.total = opt->n_traj;
-      int64_t grain = opt->n_traj / ((int64_t)n_dev * 8);          // ~8 pieces per device
-      grain = std::max<int64_t>(grain, 1 << 16);                     // but never tiny launches
+      int64_t grain = opt->n_traj / ((int64_t)n_dev * 4);          // ~4 pieces per device
+      grain = std::max<int64_t>(grain, 1 << 19);                     // but never launches too small to fill a GPU
       src.grain = (grain + 31) & ~(int64_t)31;
     } else {
       src.lo = opt->n_traj * g / n_dev;
