@@ -1,5 +1,8 @@
+"""Development aid: end-to-end latency of small ensembles (config 1 size) through the Python mirror."""
 import sys, time, numpy as np
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import simplediffeq_b200 as S
 n = 10000
 u0 = np.zeros((3, n)); u0[0] = 1
