@@ -729,8 +729,13 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSour
               (long long)piece, n_buf, (double)pooled / 1048576.0, ms_since(t_phase));
     }
     int64_t c0 = 0, c1 = 0;
-    for (int i = 0; src.next(piece, &c0, &c1); ++i) {
+    for (int i = 0;; ++i) {
       const int b = i % n_buf;
+      // dynamic ranges: a device asks for more work only when one of its buffer sets is free again --
+      // launches are asynchronous, so without this the first host thread to finish its setup would
+      // drain the shared cursor before the other devices have created their streams
+      if (src.shared) SDE_TRY(cudaStreamSynchronize(st[b]));
+      if (!src.next(piece, &c0, &c1)) break;
       const Buffers& B = buf[b];
       cudaStream_t s_ = st[b];
       const int64_t n = c1 - c0;
