@@ -599,19 +599,28 @@ int launch(sde_system_s* sys, const sde_options_t* o, const void* d_u0, const vo
 // Source of contiguous trajectory ranges for one device of a host-buffer solve.
 //   static : the device owns [lo, hi) = [floor(gN/G), floor((g+1)N/G)) and walks it in pieces that
 //            fit its memory budget (fixed-step algorithms: every trajectory costs the same);
-//   dynamic: all devices pull pieces of `grain` trajectories from one shared counter (adaptive
+//   dynamic: all devices pull pieces (guided self-scheduling, >= `grain`) from one shared counter (adaptive
 //            algorithms: step counts vary 10x along a parameter sweep, so equal index ranges are
 //            not equal work -- the host-level analogue of the kernels' work queue).
 // --------------------------------------------------------------------------------------------
 struct RangeSource {
   int64_t lo = 0, hi = 0;                    // static range (cursor = lo)
   std::atomic<int64_t>* shared = nullptr;    // dynamic: next unassigned trajectory
-  int64_t total = 0, grain = 0;
+  int64_t total = 0, grain = 0;              // dynamic: ensemble size, smallest piece handed out
+  int n_dev = 1;
+  // dynamic pieces follow guided self-scheduling: half of an equal share of what is left, never less
+  // than `grain` -- large pieces first, small ones at the end, where the imbalance is decided
+  int64_t guided_len(int64_t s) const {
+    return std::max<int64_t>(grain, (((total - s) / (2 * (int64_t)n_dev)) + 31) & ~(int64_t)31);
+  }
   bool next(int64_t max_len, int64_t* a, int64_t* b) {
     if (shared) {
-      const int64_t len = std::min(max_len, grain);
-      const int64_t s = shared->fetch_add(len);
-      if (s >= total) return false;
+      int64_t s = shared->load();
+      int64_t len;
+      do {
+        if (s >= total) return false;
+        len = std::min(max_len, guided_len(s));
+      } while (!shared->compare_exchange_weak(s, s + len));
       *a = s; *b = std::min(total, s + len);
       return true;
     }
@@ -620,7 +629,7 @@ struct RangeSource {
     lo = *b;
     return true;
   }
-  int64_t max_piece() const { return shared ? std::min(grain, total) : hi - lo; }
+  int64_t max_piece() const { return shared ? std::min(total, guided_len(0)) : hi - lo; }
 };
 
 // one device of a host-buffer solve.
@@ -682,7 +691,8 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSour
     if (const char* e = getenv("SDE_TUNE_PIECE")) want = std::max<int64_t>(32, atoll(e));   // measurement only
     piece = std::min<int64_t>(piece, std::min<int64_t>(want, range));
     if (piece > 32) piece = (piece + 31) & ~(int64_t)31;
-    const int n_buf = piece >= range ? 1 : kBuf;
+    int n_buf = piece >= range ? 1 : kBuf;
+    if (const char* e = getenv("SDE_TUNE_NBUF")) n_buf = std::max(1, std::min(kBuf, atoi(e)));   // measurement only
 
     cudaStream_t st[kBuf] = {nullptr, nullptr};
     Buffers buf[kBuf];
@@ -901,9 +911,8 @@ int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const 
     if (is_adaptive(opt->alg) && !getenv("SDE_TUNE_STATIC_SHARDS")) {   // env knob: measurement only
       src.shared = &cursor;
       src.total = opt->n_traj;
-      int64_t grain = opt->n_traj / ((int64_t)n_dev * 4);          // ~4 pieces per device
-      grain = std::max<int64_t>(grain, 1 << 19);                     // but never launches too small to fill a GPU
-      src.grain = (grain + 31) & ~(int64_t)31;
+      src.n_dev = n_dev;
+      src.grain = 1 << 19;                     // never launches too small to fill a GPU (~1.5e5 lanes in flight)
     } else {
       src.lo = opt->n_traj * g / n_dev;
       src.hi = opt->n_traj * (g + 1) / n_dev;
