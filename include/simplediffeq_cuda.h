@@ -21,6 +21,8 @@
  *       the reference's exceptions: error("dt<dtmin") src/tsit5/gpuatsit5.jl:256,
  *       src/verner/gpuvern7.jl:358, src/verner/gpuvern9.jl:466; ReturnCode.Default otherwise
  *       (test/gpu_ode_regression.jl:24-25).
+ *   sde_em_solve / sde_em_solve_device / sde_em_system_* / sde_em_noise*   (second half of this file)
+ *       DiffEqBase.solve(prob::SDEProblem{uType,tType,false}, alg::SimpleEM; dt)   src/euler_maruyama.jl:48-94
  *
  * All functions return SDE_OK (0) or a negative error code; sde_last_error() gives the message of
  * the calling thread's last failure.  Nothing throws across this boundary.  The library is
@@ -122,7 +124,8 @@ typedef struct sde_options {
                          May be NULL: then t0 + k*dt (rounded product, rounded sum) is used. */
   const void* saveat; /* SDE_SAVE_SAVEAT: HOST array of n_save times in dtype */
   int64_t n_save;
-  int64_t max_attempts; /* adaptive: 0 = unlimited like the reference */
+  int64_t max_attempts; /* adaptive: attempts (accepted + rejected) per trajectory; 0 = unlimited like the
+                           reference (the int32 range of the naccept / nreject counters) */
   int64_t out_capacity; /* adaptive SDE_SAVE_EVERYSTEP: slots per trajectory in out_u / out_t (>= 1) */
 } sde_options_t;
 
@@ -165,8 +168,10 @@ SDE_API int sde_system_prepare(sde_system_t sys, const sde_options_t* opt);
  *        fixed step: ignored (times are trajectory independent: see sde_fixed_times).
  * naccept/nreject/retcode: [n_traj] int32, each may be NULL; fixed-step algorithms write zeros
  *        (no step control, retcode Default).
- * devices/n_dev: CUDA device ordinals to shard over by contiguous trajectory ranges, one host
- *        thread + stream per device, no collective; NULL/0 = current device only. */
+ * devices/n_dev: CUDA device ordinals to shard over, one host thread per device, no collective;
+ *        NULL/0 = current device only.  Fixed-step algorithms: contiguous index ranges
+ *        [g*N/G, (g+1)*N/G).  Adaptive algorithms: contiguous pieces handed out from a shared cursor
+ *        (step counts are not uniform along a sweep).  Results do not depend on the assignment. */
 SDE_API int sde_solve(sde_system_t sys, const sde_options_t* opt, const void* u0, const void* p,
               void* out_u, void* out_t, int32_t* naccept, int32_t* nreject, int32_t* retcode,
               const int* devices, int n_dev);
