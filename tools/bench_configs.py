@@ -176,8 +176,30 @@ def other_system_configs():
                  failed=int((r["retcode"] != 0).sum().item()))
 
 
+def everystep_configs():
+    """GPUSimpleRK4 / GPUSimpleEuler keep every state in the reference (src/rk4/gpurk4.jl:66-68,84,
+    src/euler/gpueuler.jl): their natural roofline is HBM write bandwidth."""
+    n, steps = 1 << 22, 500
+    u0, p = lorenz(n)
+    for alg in (S.GPUSimpleRK4(), S.GPUSimpleEuler(), S.GPUSimpleTsit5()):
+        for layout, nm in ((1, "soa"), (0, "traj_major_staged")):
+            out = torch.empty((n, steps + 1, 3) if layout == 0 else (steps + 1, 3, n), dtype=torch.float64, device=DEV)
+            ms, r = timed(lambda: S.solve_device(L_SYS(), alg, u0, p, (0.0, 0.5), dt=1e-3, save_mode=2, layout=layout, out=out, stats=False, sync=False), reps=3)
+            gbs = n * (steps + 1) * 24 / ms / 1e6
+            emit(config="every step %s Lorenz 4Mi x %d steps %s f64" % (type(alg).__name__, steps, nm), ms=ms, hbm_gbs=gbs,
+                 hbm_frac=gbs / HBM, steps_per_s=n * steps / ms * 1e3)
+            del out, r
+            torch.cuda.empty_cache()
+
+
+def L_SYS():
+    return S.systems.lorenz
+
+
 if __name__ == "__main__":
-    if "--others" in sys.argv:
+    if "--everystep" in sys.argv:
+        everystep_configs()
+    elif "--others" in sys.argv:
         other_system_configs()
     elif "--adaptive-saveat" in sys.argv:
         adaptive_saveat_configs()
