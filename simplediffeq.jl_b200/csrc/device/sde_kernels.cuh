@@ -171,16 +171,30 @@ struct SeriesWriter {
   __device__ __forceinline__ void flush(int cnt) {
     __syncwarp();
     const int per = kFull ? Cfg::S * N : cnt * N;    // elements per trajectory in this flush
-    const int total = 32 * per;
     T* const row0 = a.out_u + (warp_traj0 * a.n_out + slot0) * N;   // row of the warp's first trajectory
     const i64 row_stride = a.n_out * N;
     const int n_valid = (int)((a.n_traj - warp_traj0) < 32 ? (a.n_traj - warp_traj0) : 32);
-#pragma unroll 5
-    for (int k = lane; k < total; k += 32) {
-      const int tr = k / per;
-      const int off = k - tr * per;
-      const T v = buf[tr * Cfg::LS + off];
-      if (tr < n_valid) row0[tr * row_stride + off] = v;
+    // each half-warp writes one trajectory's run per pass: 16 consecutive elements per instruction
+    // (128 B for doubles), ceil(per/16) instructions per run, and the row pointer advances by a plain
+    // 64-bit add -- no per-element division / index arithmetic (the element-linear loop this replaces
+    // spent ~12 instructions per 8-byte store, as many as the integration between two flushes)
+    const int half = (int)(lane >> 4), l16 = (int)(lane & 15u);
+    const T* src = buf + half * Cfg::LS + l16;
+    T* dst = row0 + half * row_stride + l16;
+    constexpr int kPasses = (Cfg::S * N + 15) / 16;
+#pragma unroll 4
+    for (int r = half; r < 32; r += 2) {
+      if (r < n_valid) {
+        if (kFull) {
+#pragma unroll
+          for (int j = 0; j < kPasses; ++j)
+            if (j * 16 + 16 <= Cfg::S * N || j * 16 + l16 < Cfg::S * N) dst[j * 16] = src[j * 16];
+        } else {
+          for (int off = l16; off < per; off += 16) dst[off - l16] = src[off - l16];
+        }
+      }
+      src += 2 * Cfg::LS;
+      dst += 2 * row_stride;
     }
     __syncwarp();
     slot0 += cnt;
@@ -246,6 +260,28 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
       cur = 1;
     }
   }
+  // the step of the next save point and its dense-output weights are fetched one save point ahead
+  // (uniform, L1-resident loads whose latency would otherwise sit between the step and its stores)
+  // (the weights only in the staged kernels: shared memory already caps those at 4 CTAs per SM, whereas
+  //  the SoA kernel would lose a CTA per SM to the extra registers -- measured: 90 % -> 81 % of HBM peak)
+  constexpr int kNever = 0x7fffffff;
+  constexpr bool kPrefetchB = STAGED;
+  int next_save_step = kNever;
+  T b_next[kPrefetchB ? Method::kNB : 1];
+  auto fetch_plan = [&]() {
+    if (SAVE == kSaveAt) {
+      if (cur < a.n_save) {
+        next_save_step = a.plan_step[cur];
+        if (kPrefetchB) {
+#pragma unroll
+          for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
+        }
+      } else {
+        next_save_step = kNever;
+      }
+    }
+  };
+  fetch_plan();
   const T dt = a.dt;
   for (i64 s = 1; s <= a.n_steps; ++s) {
 #pragma unroll
@@ -257,18 +293,19 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     if (SAVE == kSaveEveryStep) w.put(u);
     if (SAVE == kSaveAt) {
       bool prepared = false;
-      while (cur < a.n_save && (i64)a.plan_step[cur] == s) {
+      while ((i64)next_save_step == s) {
         if (!prepared) {           // extra stages do not depend on theta: once per step
           m.template dense_prepare<Q2>(uprev, p, t, dt);   // time base = advanced t (Q3)
           prepared = true;
         }
         T b[Method::kNB];
 #pragma unroll
-        for (int j = 0; j < Method::kNB; ++j) b[j] = a.plan_b[(i64)cur * Method::kNB + j];
+        for (int j = 0; j < Method::kNB; ++j) b[j] = kPrefetchB ? b_next[j] : a.plan_b[(i64)cur * Method::kNB + j];
+        ++cur;
+        fetch_plan();
         T o[N];
         m.template dense_combine<Q2>(b, dt, uprev, o);
         w.put(o);
-        ++cur;
       }
     }
   }

@@ -96,7 +96,12 @@ def main():
     u0, p = lorenz(1_000_000)
     adaptive("4: Lorenz 1M AVern9 tol 1e-12", L, S.GPUSimpleAVern9(), u0, p, (0.0, 10.0), 1e-12, 520)
     adaptive("4b: Lorenz 1M AVern7 tol 1e-10", L, S.GPUSimpleAVern7(), u0, p, (0.0, 10.0), 1e-10, 320)
+    config5()
+
+
+def config5():
     # config 5: 4 M Lorenz, Tsit5 + saveat 0:0.01:10
+    L = S.systems.lorenz
     n = 4_000_000
     u0, p = lorenz(n)
     saveat = S.jl_range(0.0, 0.01, 10.0)
@@ -197,7 +202,9 @@ def L_SYS():
 
 
 if __name__ == "__main__":
-    if "--everystep" in sys.argv:
+    if "--config5" in sys.argv:
+        config5()
+    elif "--everystep" in sys.argv:
         everystep_configs()
     elif "--others" in sys.argv:
         other_system_configs()
