@@ -295,3 +295,27 @@ def test_fixed_times_match_the_reference_rules(sde):
     assert np.array_equal(sde.api.fixed_times(o, np.float64), g)
     o = sde.api.make_options(sde.GPUSimpleTsit5(), np.dtype(np.float64), 1, (0.0, 1.0), 0.1, 0, 0, None, 0, 0, 0, 0, keep)
     assert list(sde.api.fixed_times(o, np.float64)) == [0.0, g[9] + 0.1]
+
+
+def test_fixed_times_match_reference_source_execution(sde):
+    """`sol.t` of the fixed-step solves (sde_fixed_times + the Julia range restatement, host code only)
+    against the times the reference's own source produced (tests/golden/golden_jlmini_v1.json)."""
+    import jlmini_cases as J
+    from common import bits_equal
+    api = sde.api if hasattr(sde, "api") else __import__("simplediffeq_b200.api", fromlist=["api"])
+    checked = 0
+    for case in J.load_cases():
+        if case["alg"] in J.ADAPTIVE or "error" in case:
+            continue
+        a = J.case_inputs(case)
+        exp_t, _ = J.expected(case)
+        alg = getattr(sde, case["alg"])()
+        mode = {"endpoint": 0, "saveat": 1, "everystep": 2}[a["kind"]]
+        keep = []
+        o = api.make_options(alg, np.dtype(a["dtype"]), 1, (a["t0"], a["tf"]), a["dt"], a["abstol"], a["reltol"],
+                             a["saveat"], mode, 0, 0, 0, keep)
+        t = api.fixed_times(o, a["dtype"])
+        assert len(t) == len(exp_t), case["name"]
+        assert bits_equal(t.astype(exp_t.dtype), exp_t), case["name"]     # ts has eltype(dt) (quirk Q11)
+        checked += 1
+    assert checked >= 50
