@@ -11,6 +11,8 @@ restatement (oracle/oracle.cpp), this module EXECUTES THE REFERENCE'S OWN SOURCE
 reference's tests (`test/gpusimpleatsit5_tests.jl:3-13`, `test/gpu_ode_regression.jl:2-4`) and
 evaluates them with IEEE Float64 / Float32 scalars.  `oracle/jlmini/gen_golden.py` turns the
 results into fixtures under tests/golden/ which pin the C++ oracle (tests/test_oracle_jlmini.py).
+The out-of-place SimpleEM method of `src/euler_maruyama.jl:46-94` is executed the same way
+(`gen_golden_em.py`, with `randn` supplied by the caller) and pins oracle/oracle_em.cpp.
 
 What is NOT the reference's text and therefore restated here ([EXT], same assumptions A1-A9 as
 SURVEY.md section 8c; each is one small function below so that it can be flipped):
@@ -427,12 +429,18 @@ class Parser:
             if braces:
                 self.next()
             while True:
+                if braces:
+                    self.skip_only_nl()
+                    if self.is_op("}"):      # trailing comma: `where {\n uType,\n tType,\n }`
+                        break
                 tv = self.next().val
                 bound = None
                 if self.is_op("<:"):
                     self.next()
                     bound = self.parse_postfix()
                 where[tv] = bound
+                if braces:
+                    self.skip_only_nl()
                 if self.is_op(","):
                     self.next()
                     continue
@@ -475,6 +483,9 @@ class Parser:
 
     def parse_cmp(self):
         a = self.parse_range()
+        if self.peek().kind == "id" and self.peek().val == "isa":     # `x isa T`
+            self.next()
+            return ("isa", a, self.parse_range())
         if self.peek().kind == "op" and self.peek().val in _CMP_OPS:
             operands, ops = [a], []
             while self.peek().kind == "op" and self.peek().val in _CMP_OPS:
@@ -673,6 +684,21 @@ class Parser:
                 self.expect_op(")")
                 return ("paren", e)
             if tok.val == "[":
+                save = self.i
+                self.skip_only_nl()
+                if not self.is_op("]"):
+                    first = self.parse_expr()
+                    if self.is_kw("for"):     # comprehension [expr for v in iter]
+                        self.next()
+                        var = self.next()
+                        if not (self.is_kw("in") or self.is_op("=")):
+                            self.err("comprehension: `in` expected")
+                        self.next()
+                        it = self.parse_expr()
+                        self.skip_only_nl()
+                        self.expect_op("]")
+                        return ("comprehension", first, var.val, it)
+                self.i = save
                 args, _ = self.parse_call_args("]")
                 return ("vect", args)
             if tok.val == ":":   # symbol literal
@@ -681,7 +707,7 @@ class Parser:
         self.err("expression expected")
 
 
-def parse_definitions(src, fname, wanted=None):
+def parse_definitions(src, fname, wanted=None, first_only=False):
     """Parse the top-level `function` / `struct` definitions of a file (optionally preceded by macros
     such as @muladd / @inline); everything else at top level is skipped line by line."""
     toks = tokenize(src)
@@ -702,7 +728,7 @@ def parse_definitions(src, fname, wanted=None):
                 while p.t[j + 1].kind == "op" and p.t[j + 1].val == ".":
                     j += 2
                     nm = p.t[j].val
-                if nm not in wanted:
+                if nm not in wanted or (first_only and any(d[0][0] == "function" and d[0][1] == nm for d in defs)):
                     p.i = start
                     _skip_definition(p)
                     continue
@@ -969,6 +995,15 @@ class Problem:
         self.f, self.u0, self.tspan, self.p = f, u0, tuple(tspan), p
 
 
+class SDEProblem:
+    """SciMLBase.SDEProblem{uType, tType, false}: f, g, u0, tspan, p (diagonal noise: no noise_rate_prototype)."""
+
+    def __init__(self, f, g, u0, tspan, p=None, noise_rate_prototype=None):
+        self.f, self.g, self.u0, self.tspan, self.p = f, g, u0, tuple(tspan), p
+        self.noise_rate_prototype = noise_rate_prototype
+        self.iip = False
+
+
 class Solution:
     def __init__(self, t, u):
         self.t, self.u = t, u
@@ -1186,8 +1221,18 @@ class Interp:
             "has_analytic": lambda f: False,
             "calculate_solution_errors!": lambda *a, **k: None,
             "SVector": "SVector", "MVector": "MVector", "Vector": "Vector", "SArray": self._sarray,
-            "ODEProblem": "ODEProblem", "Type": "Type",
+            "ODEProblem": "ODEProblem", "Type": "Type", "Number": "Number", "Real": "Real",
+            # SimpleEM (src/euler_maruyama.jl): Julia's task-local `randn` is not reproducible outside
+            # its process, so the normals are handed in by the caller (self.randn_hook)
+            "is_diagonal_noise": lambda prob: prob.noise_rate_prototype is None,
+            "randn": lambda *a: self.randn_hook(*a),
+            "size": lambda x, d: x.shape[d - 1],
         })
+        self.randn_hook = self._no_randn
+
+    @staticmethod
+    def _no_randn(*a):
+        raise JlRuntimeError("randn called without a noise source (set Interp.randn_hook)")
 
     # ---- builtins
     @staticmethod
@@ -1228,9 +1273,11 @@ class Interp:
         return x
 
     # ---- loading definitions
-    def load(self, path, wanted=None, force_muladd=()):
+    def load(self, path, wanted=None, force_muladd=(), first_only=False):
+        """first_only: take only the first method of each wanted name (euler_maruyama.jl: the out-of-place
+        method; the in-place one that follows uses broadcast-assignment macros outside the subset)."""
         src = open(path, encoding="utf-8").read()
-        for node, macros, line in parse_definitions(src, os.path.basename(path), wanted):
+        for node, macros, line in parse_definitions(src, os.path.basename(path), wanted, first_only):
             if node[0] == "struct":
                 _, name, tparams, fields = node
                 self.globals.vars[name] = StructType(name, tparams, fields)
@@ -1273,6 +1320,11 @@ class Interp:
             base = ann[1][1]
             if base == "Type":
                 return isinstance(val, JlType)
+            if base == "SDEProblem":            # SDEProblem{uType, tType, isinplace}
+                if not isinstance(val, SDEProblem):
+                    return False
+                iip = ann[2][2] if len(ann[2]) > 2 else None
+                return iip is None or iip[0] != "id" or iip[1] not in ("true", "false") or (iip[1] == "true") == val.iip
             if base == "SVector":
                 n = ann[2][0]
                 return isinstance(val, SVec) and (n[0] != "num" or len(val) == int(n[1]))
@@ -1285,9 +1337,12 @@ class Interp:
         cands = []
         for m in fn.methods:
             params = m[0]
-            if len(params) != len(args):
+            if params and params[-1][3]:          # trailing `args...` absorbs the remaining positionals
+                if len(args) < len(params) - 1:
+                    continue
+            elif len(params) != len(args):
                 continue
-            if all(self._matches(pt, a, m[2]) for (pn, pt, pd, ps), a in zip(params, args)):
+            if all(self._matches(pt, a, m[2]) for (pn, pt, pd, ps), a in zip(params, args) if not ps):
                 cands.append(m)
         if not cands:
             raise JlRuntimeError("MethodError: no method of %s matches %r" % (fn.name, [type(a).__name__ for a in args]))
@@ -1296,6 +1351,9 @@ class Interp:
             cands.sort(key=lambda m: -sum(1 for p in m[0] if p[1] is not None))
         params, kwparams, where, body, line, fname = cands[0]
         env = Env(self.globals)
+        if params and params[-1][3]:
+            env.vars[params[-1][0]] = tuple(args[len(params) - 1:])
+            params = params[:-1]
         # bind `where` type variables used as `::Type{T}` / `x::T`
         for (pn, pt, pd, ps), a in zip(params, args):
             if pn is not None:
@@ -1586,6 +1644,24 @@ class Interp:
             return TypeApp(base, params)
         if kind == "typed":
             return self.eval(node[1], env)
+        if kind == "isa":
+            val, T = self.eval(node[1], env), self.eval(node[2], env)
+            if T in ("Number", "Real"):
+                return is_float(val) or isinstance(val, (int, np.integer)) and not isinstance(val, (bool, np.bool_))
+            if isinstance(T, JlType):
+                return not isinstance(val, (SVec, JlVector)) and typeof_scalar(val) is T
+            raise JlRuntimeError("isa: unsupported type %r" % (T,))
+        if kind == "comprehension":
+            it = self.eval(node[3], env)
+            if not isinstance(it, UnitRange):
+                raise JlRuntimeError("comprehension over %r" % (it,))
+            items = []
+            for x in range(it.a, it.b + 1):
+                inner = Env(env)
+                inner.vars[node[2]] = x
+                items.append(self.eval(node[1], inner))
+            scalar = items and not isinstance(items[0], (SVec, JlVector))
+            return JlVector(items, eltype=typeof_scalar(items[0]) if scalar else None)
         if kind == "call":
             return self.eval_call(node, env)
         if kind == "macro":

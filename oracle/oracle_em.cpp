@@ -3,10 +3,14 @@
 //
 // *** TEST INFRASTRUCTURE ONLY *** (same rules as oracle.cpp: loaded by tests/ and smoke() only).
 //
-// PARITY STATUS: "parity unpinned", and for this row necessarily so.  The reference draws its noise
-// from Julia's task-local default RNG (`randn(typeof(u0))`, src/euler_maruyama.jl:76-85), which is
-// not reproducible outside that Julia process, and its own tests (test/simpleem_tests.jl) only check
-// `sol.t == collect(0:0.25:1.0)` and `length(sol.u) == 5`.  So:
+// PARITY STATUS: step arithmetic pinned to the reference's own SOURCE TEXT; noise necessarily not.
+// The reference draws its noise from Julia's task-local default RNG (`randn(typeof(u0))`,
+// src/euler_maruyama.jl:76-85), which is not reproducible outside that Julia process, and its own tests
+// (test/simpleem_tests.jl) only check `sol.t == collect(0:0.25:1.0)` and `length(sol.u) == 5`.  So:
+//   * oracle/jlmini parses and executes src/euler_maruyama.jl:46-94 (its @muladd rewriting included) with
+//     `randn` replaced by a supplied list of normals; oracle_em_solve reproduces those outputs BIT FOR
+//     BIT for scalar and diagonal SVector states, FP64 and FP32 (tests/golden/golden_jlmini_em_v1.json,
+//     tests/test_oracle_em_jlmini.py); the non-diagonal branch is outside that pin (assumption A11);
 //   * the STEP ARITHMETIC is restated here with the increments dW handed in as data
 //     (oracle_em_solve), which makes it comparable bit for bit with the CUDA kernel given the same
 //     normals, and against closed-form results (noise-free limit, exact GBM path, strong order 1/2);

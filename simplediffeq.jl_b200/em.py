@@ -120,15 +120,32 @@ def em_steps(tspan, dt, dtype=np.float64):
     return int(q)
 
 
+def _round_fraction(fr, T):
+    """Round an exact rational to T (float64 / float32), nearest-even, in ONE rounding."""
+    x = float(fr)                      # CPython rounds int/int correctly to double
+    if T is np.float64:
+        return np.float64(x)
+    c = np.float32(x)                  # may be double-rounded: pick the best of c and its neighbours exactly
+    from fractions import Fraction
+    best, best_err = None, None
+    for cand in (np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))):
+        if not np.isfinite(cand):
+            continue
+        err = abs(Fraction(float(cand)) - fr)
+        even = (int(np.float32(cand).view(np.uint32)) & 1) == 0
+        if best is None or err < best_err or (err == best_err and even):
+            best, best_err = cand, err
+    return np.float32(best)
+
+
 def em_times(tspan, dt, dtype=np.float64):
-    """t = [tspan[1] + i*dt for i in 0:n-1] under @muladd = muladd(i, dt, tspan[1]) (src/euler_maruyama.jl:68)."""
+    """t = [tspan[1] + i*dt for i in 0:n-1] under @muladd = muladd(i, dt, tspan[1]) (src/euler_maruyama.jl:68):
+    one fused multiply-add per element, evaluated exactly in rational arithmetic and rounded once."""
+    from fractions import Fraction
     T = np.dtype(dtype).type
     n = em_steps(tspan, dt, dtype) + 1
-    # a correctly rounded fma: the exact product i*dt of two doubles plus t0, in extended precision
-    if np.dtype(dtype) == np.float64:
-        from fractions import Fraction
-        return np.array([float(Fraction(float(i)) * Fraction(float(dt)) + Fraction(float(tspan[0]))) for i in range(n)])
-    return (np.arange(n, dtype=np.float64) * np.float64(T(dt)) + np.float64(T(tspan[0]))).astype(np.float32)
+    fdt, ft0 = Fraction(float(T(dt))), Fraction(float(T(tspan[0])))
+    return np.array([_round_fraction(Fraction(i) * fdt + ft0, T) for i in range(n)], dtype=T)
 
 
 class EMEnsembleSolution:

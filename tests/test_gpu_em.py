@@ -172,3 +172,26 @@ def test_em_committed_golden_vectors(sde):
         got = sde.solve_em_arrays(getattr(sde.sde_systems, case["system"]), u0, p, case["t0"], case["dt"], case["n_steps"],
                                   noise=z, layout=0)
         assert _bits(got, want), (case["system"], case["dtype"])
+
+
+# ---- CUDA path vs the reference's OWN SOURCE TEXT (src/euler_maruyama.jl executed by oracle/jlmini with
+# the normals supplied; tests/golden/golden_jlmini_em_v1.json).  Reads like test/simpleem_tests.jl:
+# solve(SDEProblem(f, g, u0, tspan, p), SimpleEM(); dt) -> sol.t, sol.u.
+import jlmini_em_cases as JE  # noqa: E402
+
+_JE_CASES = JE.load_cases()
+
+
+@pytest.mark.parametrize("case", _JE_CASES, ids=[c["name"] for c in _JE_CASES])
+def test_em_cuda_path_vs_reference_source_execution(sde, case):
+    T, u0, p, t0, tf, dt = JE.inputs(case)
+    prob = sde.SDEProblem(getattr(sde.sde_systems, case["system"]), u0, (t0, tf), p)
+    if "error" in case:
+        with pytest.raises(ValueError, match="InexactError"):      # Julia: Int(3.3333333333333335)
+            sde.solve_em(prob, sde.SimpleEM(), dt=dt)
+        return
+    exp_t, exp_u, z = JE.expected(case)
+    sol = sde.solve_em(prob, sde.SimpleEM(), dt=dt, noise=z[:, :, None] if len(z) else None)
+    assert len(sol.u) == case["n_out"] and len(sol.t) == case["n_out"]
+    assert _bits(np.asarray(sol.t, dtype=T), exp_t)
+    assert _bits(np.asarray(sol.u, dtype=T).reshape(exp_u.shape), exp_u)

@@ -136,6 +136,65 @@ def test_control_flow_and_functions():
     assert it.call(it.globals.vars["sumto"], [5]) == 1 + 2 + 4 + 5
 
 
+def test_simpleem_constructs():
+    """What src/euler_maruyama.jl needs beyond the ODE solvers: a trailing `args...`, `where {\n T,\n}`,
+    SDEProblem{uType,tType,false} dispatch, comprehensions, `isa`, Int() with InexactError, randn hook."""
+    src = '''
+    @muladd function em(
+            prob::SDEProblem{uType, tType, false}, alg::SimpleEM,
+            args...;
+            dt = error("dt required for SimpleEM"),
+            kwargs...
+        ) where {
+            uType,
+            tType,
+        }
+        u0 = prob.u0
+        tspan = prob.tspan
+        n = Int((tspan[2] - tspan[1]) / dt) + 1
+        u = [u0 for i in 1:n]
+        t = [tspan[1] + i * dt for i in 0:(n - 1)]
+        for i in 2:n
+            if u0 isa Number
+                u[i] = u[i - 1] + 2 * dt + dt * 3 * randn(typeof(u0))
+            else
+                u[i] = u[i - 1] + dt * 3 .* randn(typeof(u0))
+            end
+        end
+        return t, u, length(args)
+    end
+    '''
+    it = M.Interp()
+    for node, macros, line in M.parse_definitions(src, "<t>"):
+        assert macros == ["muladd"]
+        fn = it.globals.vars.setdefault(node[1], M.Function(node[1]))
+        fn.methods.append((node[2], node[3], node[4], M.to_muladd(node[5]), line, "<t>"))
+    F = np.float64
+    seq = iter([F(1.0), F(-1.0), F(0.5), F(0.25)] * 4)
+    it.randn_hook = lambda ty: (M.SVec(next(seq) for _ in range(int(ty.params[0]))) if isinstance(ty, M.TypeApp) else next(seq))
+    alg = M.Struct("SimpleEM", [], [])
+    prob = M.SDEProblem(None, None, F(0.5), (F(1.0), F(2.0)))
+    t, u, nargs = it.call(it.globals.vars["em"], [prob, alg], {"dt": F(0.5)})
+    assert [float(x) for x in t.items] == [1.0, 1.5, 2.0] and nargs == 0
+    assert [float(x) for x in u.items] == [0.5, 0.5 + 1.0 + 1.5, 3.0 + 1.0 - 1.5]
+    t, u, nargs = it.call(it.globals.vars["em"], [prob, alg, 7, 8], {"dt": F(0.5)})      # args... absorbs extras
+    assert nargs == 2
+    vprob = M.SDEProblem(None, None, M.SVec([F(0.0), F(1.0)]), (F(0.0), F(0.5)))
+    t, u, _ = it.call(it.globals.vars["em"], [vprob, alg], {"dt": F(0.5)})
+    assert [float(x) for x in u.items[1].v] == [1.5 * 1.0, 1.0 + 1.5 * -1.0]     # (dt * 3) .* z, z = (1, -1)
+    with pytest.raises(M.JlError, match="InexactError"):
+        it.call(it.globals.vars["em"], [prob, alg], {"dt": F(0.3)})
+    with pytest.raises(M.JlError, match="dt required"):
+        it.call(it.globals.vars["em"], [prob, alg], {})
+    iip = M.SDEProblem(None, None, F(0.5), (F(1.0), F(2.0)))
+    iip.iip = True
+    with pytest.raises(M.JlRuntimeError, match="MethodError"):
+        it.call(it.globals.vars["em"], [iip, alg], {"dt": F(0.5)})
+    # the time grid is muladd(i, dt, tspan[1]): one rounding
+    n = M.to_muladd(_parse_expr("[tspan[1] + i * dt for i in 0:(n - 1)]"))
+    assert n[0] == "comprehension" and n[1][0] == "muladd"
+
+
 def test_golden_file_is_what_the_reference_source_produces():
     """When the reference tree is present (build container), re-execute a sample of the committed
     fixture's cases and require identical bits -- the fixture is not hand-edited."""
