@@ -15,8 +15,11 @@ ALWAYS_EVERYSTEP = ("GPUSimpleRK4", "GPUSimpleEuler")
 F01 = np.float32(0.1)
 
 
-def load_cases():
-    with open(PATH) as fh:
+RANDOM_PATH = os.path.join(HERE, "golden", "golden_jlmini_random_v1.json")
+
+
+def load_cases(path=PATH):
+    with open(path) as fh:
         return json.load(fh)["cases"]
 
 
