@@ -1,6 +1,7 @@
 // Development aid: times one adaptive kernel instantiation directly (no library rebuild needed), for
 // tuning experiments.  nvcc -O3 -std=c++17 -fmad=false -gencode arch=compute_100a,code=sm_100a
 //   [-DMINB=n] [-DSYS=VanDerPol -DNSTATE=2 -DNPAR=1] [-DMETHOD=Vern9Method -DV9=true]
+// run: ./a.out [tol] [sorted: 0|1 (Van der Pol)] [log2 n] [max persistent CTAs per SM, 0 = occupancy]
 #include <cstdio>
 #include <vector>
 #include <cuda_runtime.h>
@@ -41,6 +42,8 @@ int main(int argc, char** argv) {
   a.out_u = dout; a.ld_out = n; a.n_out = 1; a.naccept = na; a.nreject = nr; a.queue = q;
   int per_sm = 0, sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0);
+  const int occ = per_sm;
+  if (argc > 4 && atoi(argv[4]) > 0 && atoi(argv[4]) < per_sm) per_sm = atoi(argv[4]);   // cap persistent CTAs per SM
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e9;
@@ -51,7 +54,7 @@ int main(int argc, char** argv) {
   }
   std::vector<int> hna(n), hnr(n); cudaMemcpy(hna.data(), na, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hnr.data(), nr, n * 4, cudaMemcpyDeviceToHost);
   double acc = 0, rej = 0; for (long long i = 0; i < n; ++i) { acc += hna[i]; rej += hnr[i]; }
-  printf("%s n=%lld regs=%d blocks/SM=%d block=%d: %.3f ms  attempts/s=%.4g (acc %.0f rej %.0f) %s\n", argv[0], n, fa.numRegs, per_sm, BLOCK, best,
+  printf("%s tol=%g n=%lld regs=%d occupancy=%d CTAs/SM=%d block=%d: %.3f ms  attempts/s=%.4g (acc %.0f rej %.0f) %s\n", argv[0], tol, n, fa.numRegs, occ, per_sm, BLOCK, best,
          (acc + rej) / best * 1e3, acc, rej, cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
