@@ -328,6 +328,17 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
 //   kV9   AVern9: dtmin / tf-snap thresholds are 1.0f-7 (quirk Q4) and extra-stage times use told
 //   kStrict  literal controller arithmetic (pow, divisions, sqrt) instead of the log2-domain one
 // ------------------------------------------------------------------------------------------
+// `b`, in a form that ptxas can neither relate to the predicate it came from nor evaluate before `x` is known.
+// `zero` is 0 at run time (a bit of KArgs::compat that the launcher always clears) but a kernel parameter
+// to the compiler.  Why: ptxas hoists the convergence-barrier BREAK of the rejecting lanes to the instruction
+// that computes `accept`, and a warp whose lanes disagree then runs the controller code that BOTH outcomes
+// share once per group (ncu source counters, shuffled Van der Pol sweep: that block was executed 1.32x per
+// attempt; AVern9 at tol 1e-12, 13 % rejections: ~2x).  Branching on this copy moves the divergence behind
+// the shared code for 3 instructions: +4 % on the shuffled Van der Pol sweep and on AVern9, -1 % where
+// rejections are rare (profiles/r1_adaptive_late_branch_ab.txt).
+__device__ __forceinline__ bool late_flag(bool b, double x, int zero) { return b != ((__double2hiint(x) & zero) != 0); }
+__device__ __forceinline__ bool late_flag(bool b, float x, int zero) { return b != ((__float_as_int(x) & zero) != 0); }
+
 template <class Sys, class T, class Method, int SAVE, bool kV9, bool kStrict>
 __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP;
@@ -409,11 +420,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
     }
 
     if (active) {
-      int ret = -1;
+      bool fin = false;          // trajectory finished (or failed) in this attempt
+      int ret = kRetDefault;
       if ((double)dt < thr) {
-        ret = kRetDtMin;                               // error("dt<dtmin")
+        fin = true; ret = kRetDtMin;                   // error("dt<dtmin")
       } else if (nacc + nrej >= attempt_limit) {
-        ret = kRetMaxIters;
+        fin = true; ret = kRetMaxIters;
       } else {
         m.template stages<true>(uprev, u, p, t, dt);
         T e[N];
@@ -499,7 +511,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           }
           dt = (T)((double)dt * sde_exp2_fast(-lx, zlane));
         }
-        if (!accept) {
+        if (!late_flag(accept, dt, a.compat & kCompatRuntimeZero)) {
           ++nrej;
         } else {
           const T rem = tf - t - dtold;
@@ -529,7 +541,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
               ++cur;
             }
           }
-          if (!(t < tf)) ret = kRetDefault;
+          fin = !(t < tf);
           // the next step starts from the accepted state (after the dense output, which reads the
           // old uprev / k1)
 #pragma unroll
@@ -537,7 +549,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           m.begin_step();
         }
       }
-      if (ret >= 0) {   // trajectory finished (or failed): publish and free the lane
+      if (fin) {   // publish and free the lane
         if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
         if (SAVE == kSaveAt && cur < a.n_save) {   // never reached (failure, or saveat beyond tf)
           T nanv[N];

@@ -148,6 +148,8 @@ int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
     return fail(SDE_ERR_INVALID, "unknown layout %d", o->layout);
   if (o->n_traj < 0) return fail(SDE_ERR_INVALID, "n_traj < 0");
+  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER))
+    return fail(SDE_ERR_INVALID, "unknown compat flags 0x%x", (unsigned)o->compat);
   if (o->save_mode == SDE_SAVE_SAVEAT) {
     if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(SDE_ERR_INVALID, "saveat array missing");
     if (o->n_save > 0x7fffffff) return fail(SDE_ERR_INVALID, "n_save too large");
@@ -522,7 +524,7 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   a.t0 = (T)o->t0; a.tf = (T)o->tf; a.dt = (T)o->dt; a.abstol = (T)o->abstol; a.reltol = (T)o->reltol;
   a.n_steps = adaptive ? 0 : o->n_steps;
   a.n_save = o->save_mode == SDE_SAVE_SAVEAT ? (int)o->n_save : 0;
-  a.compat = o->compat;
+  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER);   // bit 30 must reach the kernel as 0 (sde::kCompatRuntimeZero)
   a.layout = o->layout;
   a.max_attempts = o->max_attempts;
   a.out_u = (T*)d_out_u;

@@ -136,6 +136,12 @@ def test_option_validation_errors(sde):
     o.alg, o.dtype = 0, 7
     assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == -1
     assert L.sde_system_prepare(None, ctypes.byref(o)) == -1
+    o.dtype = 0
+    assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == 0
+    for bad in (4, 0x40000000):          # unknown compat bits (bit 30 must reach the kernels as 0: sde::late_flag)
+        o.compat = bad
+        assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == -1
+        assert b"compat" in L.sde_last_error()
 
 
 def test_no_cpu_fallback_fails_loudly_without_gpu(sde):
