@@ -208,6 +208,9 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own messages (e.g. the "NCCL version ..." line that
+        # NCCL_DEBUG=VERSION prints to stdout on some boxes) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
