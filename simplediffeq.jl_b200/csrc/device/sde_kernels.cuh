@@ -159,12 +159,16 @@ struct SeriesWriter {
   i64 slot0;     // slot index of the first staged slot
   i64 warp_traj0;
   unsigned lane;
+  // direct stores: a running element offset instead of re-deriving (slot * N + c) * ld_out + traj at every put()
+  i64 off;       // element offset of the next slot (warp-uniform: lives in the uniform datapath)
 
   __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
-      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0) {
+      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0), off(0) {
     lane = threadIdx.x & 31u;
     warp_traj0 = traj - lane;
-    if (STAGED) buf = reinterpret_cast<T*>(sde_dyn_smem) + (threadIdx.x >> 5) * (32 * Cfg::LS);
+    if (STAGED) {
+      buf = reinterpret_cast<T*>(sde_dyn_smem) + (threadIdx.x >> 5) * (32 * Cfg::LS);
+    }
   }
 
   template <bool kFull>
@@ -211,7 +215,22 @@ struct SeriesWriter {
       ++slot;
       if (fill == Cfg::S) flush<true>(Cfg::S);
     } else {
-      if (valid) put_series<T, N>(a, traj, slot, v);
+      // strides straight from the kernel parameters (constant-bank operands): no per-thread stride registers
+      if (a.layout == kLayoutTrajMajor) {                      // out_u[(traj * n_out + slot) * N + c]
+        if (valid) {
+          T* q = a.out_u + (traj * a.n_out * N + off);
+#pragma unroll
+          for (int c = 0; c < N; ++c) q[c] = v[c];
+        }
+        off += N;
+      } else {                                                 // out_u[(slot * N + c) * ld_out + traj]
+        if (valid) {
+          T* q = a.out_u + (off + traj);
+#pragma unroll
+          for (int c = 0; c < N; ++c) q[c * a.ld_out] = v[c];
+        }
+        off += N * a.ld_out;
+      }
       ++slot;
     }
   }
