@@ -16,7 +16,8 @@ A bench "step" = one pass of the hot path over the whole batch (= n_traj * 10 00
 One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over
 ranks.  `e2e`: the same work through the C-ABI call `sde_solve` with pinned HOST buffers (H2D of
 u0/p and D2H of the final states inside the timed region).  `roofline`: FP64 FMA pipe (this path is
-not HBM- or tensor-bound).  `cpu_baseline`: the CPU oracle (C++ restatement of the
+not HBM- or tensor-bound); `roofline_hbm_config5`: the HBM-bound saveat config (configs[4]) measured
+in the same run.  `cpu_baseline`: the CPU oracle (C++ restatement of the
 reference; Julia is not installable here) on a bounded sample, rank 0, N = 1 only.
 """
 import argparse
@@ -125,6 +126,49 @@ def cpu_oracle_rate(n_sample, n_threads, seconds_target=None):
     dt = time.perf_counter() - t0
     assert np.all(np.isfinite(r.u))
     return n_sample * N_STEPS / dt, dt
+
+
+def config5_hbm_roofline(S, torch, dev, peaks, n=None, reps=5):
+    """BASELINE.json configs[4] (the saveat-heavy, HBM-bound config) on this device:
+    Lorenz, GPUSimpleTsit5, saveat = 0:0.01:10 (1001 points), dt = 0.1 (100 steps, 10 save points per step; the
+    config does not fix dt), SoA series layout, device-resident output.  Algorithmic bytes
+    per trajectory = 48 in + 1001 * 24 out = 24 072 B; achieved = bytes / kernel time
+    (CUDA events on the launching stream; every launch rewrites the whole output, 96 GB >> L2)."""
+    from simplediffeq_b200 import _lib, jl_range
+    if n is None:      # the config's own 4 M trajectories (96.3 GB of output) when the device has the room, else 1 M
+        free, _ = torch.cuda.mem_get_info(dev)
+        n = 4_000_000 if free > 110e9 else 1_000_000
+    u0_h, p_h = lorenz_inputs_np(0, n, n)
+    d_u0, d_p = torch.from_numpy(u0_h).to(dev), torch.from_numpy(p_h).to(dev)
+    saveat = jl_range(0.0, 0.01, 10.0)
+    out = torch.empty((len(saveat), 3, n), dtype=torch.float64, device=dev)
+    alg, sysm = S.GPUSimpleTsit5(), S.systems.lorenz
+    stream = torch.cuda.current_stream(dev)
+
+    def launch():
+        S.solve_device(sysm, alg, d_u0, d_p, TSPAN, dt=0.1, saveat=saveat, save_mode=_lib.SAVE_SAVEAT,
+                       layout=_lib.LAYOUT_SOA, out=out, stats=False, sync=False)
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize(dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    evs[0].record(stream)
+    for k in range(reps):
+        launch()
+        evs[k + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    ms = float(np.mean([evs[k].elapsed_time(evs[k + 1]) for k in range(reps)]))
+    nbytes = n * (48 + len(saveat) * 24)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs") or 6555.2
+    finite = bool(torch.isfinite(out[-1]).all().item())
+    del out
+    torch.cuda.empty_cache()
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks.get("hbm_gbs") else "fallback 6555.2 GB/s",
+            "kernel": "sde::fixed_kernel<Lorenz,double,Tsit5Method,saveat,SoA>", "kernel_ms": ms,
+            "workload": "BASELINE.json configs[4] at %d trajectories: saveat=0:0.01:10, dt=0.1, SoA output (%.1f GB per launch)" % (n, nbytes / 1e9),
+            "bytes_per_trajectory": 48 + len(saveat) * 24, "launches_timed": reps, "output_finite": finite}
 
 
 def config0_atsit5(S, oracle_lib, cores, dev):
@@ -337,6 +381,10 @@ def main():
                                     "sample": "%d of 10M trajectories x 10000 steps in %.1f s, %d std::threads (C++ restatement of GPUSimpleTsit5; Julia unavailable)" % (n_s, secs, cores)}
             line["parity_spot_check"] = {"trajectories": 512, "bit_identical_to_oracle": same}
             line["config0_atsit5"] = config0_atsit5(S, oracle_lib, cores, dev)
+            try:        # second roofline of BASELINE.json's metric ("% FP64 FMA / HBM roofline"): the saveat-heavy config
+                line["roofline_hbm_config5"] = config5_hbm_roofline(S, torch, dev, peaks)
+            except Exception as e:    # e.g. not enough free memory next to another tenant: reported, never fatal
+                line["roofline_hbm_config5"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
