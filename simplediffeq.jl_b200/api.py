@@ -298,6 +298,12 @@ def fixed_times(o, dtype):
     return out[:nw.value].copy()
 
 
+# adaptive save_everystep = true on ensembles larger than EVERYSTEP_PILOT: rows are sized from a pilot sample of
+# that many trajectories, times EVERYSTEP_SLACK (see solve)
+EVERYSTEP_PILOT = 4096
+EVERYSTEP_SLACK = 1.25
+
+
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=None, reltol=None,
           saveat=None, save_everystep=True, devices=None, layout="traj_major", compat=0,
           maxiters=0, **kwargs):
@@ -351,20 +357,33 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
 
     save_mode = _save_mode(alg, saveat, save_everystep)
     lay = _lib.LAYOUT_TRAJ_MAJOR if layout == "traj_major" else _lib.LAYOUT_SOA
+    common = dict(dt=dt, abstol=abstol, reltol=reltol, compat=compat, maxiters=maxiters, devices=devices)
     capacity = 0
     if alg.adaptive and save_mode == _lib.SAVE_EVERYSTEP:
-        # variable-length output (the reference push!es every accepted step, gpuatsit5.jl:301-303):
-        # the step sequence is deterministic, so a cheap endpoint-only pass gives the exact sizes
-        first = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, dt=dt, abstol=abstol, reltol=reltol,
-                             save_mode=_lib.SAVE_ENDPOINT, compat=compat, maxiters=maxiters, devices=devices)
+        # variable-length output (the reference push!es every accepted step, gpuatsit5.jl:301-303).  The step
+        # sequence is deterministic, so an endpoint-only pass gives the sizes: over the whole ensemble when it is
+        # small, else over a pilot sample of evenly spaced trajectories (the full solve then reports the
+        # trajectories whose row was too short -- SDE_RET_OUTPUT_FULL with the needed count in naccept -- and
+        # only in that case the ensemble is solved once more with the exact capacity).
+        if n <= EVERYSTEP_PILOT:
+            sel = slice(None)
+        else:
+            sel = np.unique(np.linspace(0, n - 1, EVERYSTEP_PILOT).astype(np.int64))
+        first = solve_arrays(sysm, alg, np.ascontiguousarray(u0_soa[:, sel]), np.ascontiguousarray(p_soa[:, sel]),
+                             base.tspan, save_mode=_lib.SAVE_ENDPOINT, **common)
         if np.any(first["retcode"] == _lib.RET_DTMIN):
             raise RuntimeError("dt<dtmin")
         capacity = int(first["naccept"].max()) + 1
-    raw = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, dt=dt, abstol=abstol, reltol=reltol,
-                       saveat=saveat, save_mode=save_mode, layout=lay, compat=compat,
-                       maxiters=maxiters, devices=devices, out_capacity=capacity)
+        if n > EVERYSTEP_PILOT:
+            capacity = int(capacity * EVERYSTEP_SLACK) + 8
+    raw = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, saveat=saveat, save_mode=save_mode, layout=lay,
+                       out_capacity=capacity, **common)
     if np.any(raw["retcode"] == _lib.RET_DTMIN):
         raise RuntimeError("dt<dtmin")       # the reference throws (src/tsit5/gpuatsit5.jl:256)
+    if capacity and np.any(raw["retcode"] == _lib.RET_OUTPUT_FULL):
+        capacity = int(raw["naccept"].max()) + 1
+        raw = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, saveat=saveat, save_mode=save_mode, layout=lay,
+                           out_capacity=capacity, **common)
     sol = EnsembleSolution(n_traj=n, dtype=dtype, save_mode=save_mode, layout=lay, u0_soa=u0_soa,
                            u_raw=raw["u"], t_shared=raw["t_shared"], t_final=raw["t_final"],
                            t_series=raw["t_series"],
