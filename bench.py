@@ -269,11 +269,21 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own messages (e.g. the "NCCL version ..." line that
-        # NCCL_DEBUG=VERSION prints to stdout on some boxes) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line.  With NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL printf()s its
+        # "NCCL version ..." banner to stdout when the communicator is created (NCCL_DEBUG_FILE does not catch it):
+        # file descriptor 1 points at stderr while the process group and its first collective are set up.
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from simplediffeq_b200.sharding import shard_bounds, endpoint_stats, gather_endpoint_stats, reduce_max
     n = args.n_traj
