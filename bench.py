@@ -178,7 +178,15 @@ def config5_hbm_roofline(S, torch, dev, peaks, n=None, reps=5):
     finite = bool(torch.isfinite(out[-1]).all().item())
     del out
     torch.cuda.empty_cache()
-    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+    traffic = None      # dram read + write bytes of one launch from the committed ncu capture, if taken at this size
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_config5_traffic.json")))
+        if int(tj["n_traj"]) == n:
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic = %d)" % nbytes,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks.get("hbm_gbs") else "fallback 6555.2 GB/s",
             "kernel": "sde::fixed_kernel<Lorenz,double,Tsit5Method,saveat,SoA>", "kernel_ms": ms,
             "workload": "BASELINE.json configs[4] at %d trajectories: saveat=0:0.01:10, dt=0.1, SoA output (%.1f GB per launch)" % (n, nbytes / 1e9),
