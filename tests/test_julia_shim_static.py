@@ -153,3 +153,26 @@ def test_constants_agree_with_the_header():
     assert n_args == len(julia_struct("SdeOptions"))
     n_args = len(_split_top(re.search(r"Ref\(SdeEmOptions\((.*?)\)\)\n", SHIM, flags=re.S).group(1)))
     assert n_args == len(julia_struct("SdeEmOptions"))
+
+
+def test_python_ctypes_mirror_matches_the_header_too(sde):
+    """The tested twin of the shim (simplediffeq.jl_b200/_lib.py): struct mirrors field by field and the argument
+    count of every declared prototype, against the same parse of the header."""
+    import ctypes
+    from simplediffeq_b200 import _lib
+    c2ct = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "double": ctypes.c_double,
+            "const void*": ctypes.c_void_p}
+    for tag, cls in (("sde_options", _lib.SdeOptions), ("sde_em_options", _lib.SdeEmOptions)):
+        c_fields = header_struct(tag)
+        assert [n for n, _ in c_fields] == [n for n, _ in cls._fields_], tag
+        for (n, cty), (_, ct) in zip(c_fields, cls._fields_):
+            assert ct is c2ct[cty], "%s.%s" % (tag, n)
+    L = _lib.lib()
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.EXPORTS)
+    for name, (ret, params) in protos.items():
+        fn = getattr(L, name)
+        if params:
+            assert fn.argtypes is not None and len(fn.argtypes) == len(params), name
+        if ret == "int":
+            assert fn.restype is ctypes.c_int, name
