@@ -57,8 +57,6 @@ def header_struct(tag):
         stmt = " ".join(stmt.split())
         if not stmt:
             continue
-        mm = re.match(r"(.*?)([\w\s,]+)$", stmt.replace("*", "* "))
-        ty = " ".join(mm.group(1).split()).replace(" *", "*") if "*" in stmt else stmt.split(" ")[0] if stmt.startswith(("int", "uint", "double")) else None
         if "*" in stmt:
             ty = " ".join(stmt.rsplit("*", 1)[0].split()) + "*"
             names = [stmt.rsplit("*", 1)[1].strip()]

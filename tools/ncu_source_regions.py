@@ -37,8 +37,6 @@ def main():
         st = {c: sum(int(data[k][ix[c]]) for k in range(a, b + 1)) for c in stall_cols}
         ns = sum(int(data[k][ix["# Samples"]]) for k in range(a, b + 1))
         top = sorted(st.items(), key=lambda kv: -kv[1])[:4]
-        fp64 = sum(1 for k in range(a, b + 1) if data[k][ix["Source"]].split()[0 if not data[k][ix["Source"]].strip().startswith("@") else 1][:2] == "DF"
-                   or data[k][ix["Source"]].strip().split()[-1 if False else 0][:1] == "D" and data[k][ix["Source"]].strip().split()[0][:4] in ("DFMA", "DMUL", "DADD", "DSET"))
         print("SASS %4d..%4d (%3d instr) exec %10d  thr %5.1f  issue share %5.2f %%  samples %5.2f %%  %s" % (
             a, b, n, ie, at, share, 100.0 * ns / max(samples, 1),
             " ".join("%s=%.0f%%" % (c[6:], 100.0 * v / max(ns, 1)) for c, v in top)))
