@@ -349,3 +349,31 @@ def test_bench_reference_arm_prints_one_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""          # the other ranks exit 0 without work
+
+
+def test_prob_func_restrictions_are_checked_on_the_host(sde):
+    """The ensemble path runs ONE kernel per ensemble: prob_func may change u0 and p only.  A changed tspan, system or
+    element type is rejected before anything is launched (no GPU needed to see the error)."""
+    prob = sde.ODEProblem(sde.systems.lorenz, [1.0, 0.0, 0.0], (0.0, 1.0), [10.0, 28.0, 8 / 3])
+    bad_tspan = sde.EnsembleProblem(prob, prob_func=lambda pr, i, rep: sde.remake(pr, tspan=(0.0, 2.0)))
+    with pytest.raises(ValueError, match="only change u0 and p"):
+        sde.solve(bad_tspan, sde.GPUSimpleTsit5(), trajectories=3, dt=0.1)
+    other = sde.ODEProblem(sde.systems.lineardecay, [1.0, 1.0, 1.0], (0.0, 1.0), [10.0, 28.0, 8 / 3])
+    bad_sys = sde.EnsembleProblem(prob, prob_func=lambda pr, i, rep: other)
+    with pytest.raises(ValueError, match="only change u0 and p"):
+        sde.solve(bad_sys, sde.GPUSimpleTsit5(), trajectories=3, dt=0.1)
+    p32 = sde.ODEProblem(sde.systems.lorenz, np.array([1, 0, 0], np.float32), (0.0, 1.0), [10, 28, 8 / 3])
+    bad_type = sde.EnsembleProblem(prob, prob_func=lambda pr, i, rep: p32)
+    with pytest.raises(ValueError, match="only change u0 and p"):
+        sde.solve(bad_type, sde.GPUSimpleTsit5(), trajectories=3, dt=0.1)
+    # prob_func is called with 1-based indices and repeat = 1, like SciMLBase's batch_func
+    seen = []
+
+    def pf(pr, i, rep):
+        seen.append((i, rep))
+        if i == 3:
+            raise KeyError("stop here")     # before any device work
+        return pr
+    with pytest.raises(KeyError):
+        sde.solve(sde.EnsembleProblem(prob, prob_func=pf), sde.GPUSimpleTsit5(), trajectories=5, dt=0.1)
+    assert seen == [(1, 1), (2, 1), (3, 1)]
