@@ -1,0 +1,162 @@
+// Host emulation of the DEVICE kernel bodies (csrc/device/sde_kernels.cuh: fixed_body, adaptive_body), so that
+// the CPU test suite can run the very source the GPU runs -- stage code, save handling, work queue, step
+// controller, late accept branch -- against the oracle without a GPU.
+//
+// *** TEST INFRASTRUCTURE ONLY ***  Built and loaded by tests/test_kernel_host_emul.py; nothing in the product
+// links it and it is no CPU fallback: the library itself still fails with SDE_ERR_CUDA without a device.
+//
+// Emulation model: one thread per "warp" (lane 0 only), one thread per block.  The warp intrinsics degenerate
+// (ballot = bit 0, shuffle = identity, votes = the lane's own predicate), __shared__ arrays become locals and
+// atomicAdd a plain add, which is exact for a single thread.  The shared-memory STAGED writer needs 32 cooperating
+// lanes and is not emulated (it is covered on the GPU); everything else is.  The only arithmetic that differs
+// from the device is the seed of sde_rcp_fast: MUFU.RCP64H there, the IEEE quotient 1.0 / x here (the float seed
+// that SDE_HOST_EMULATION selects in sde_common.cuh overflows for |x| > 3.4e38, which blown-up trajectories reach;
+// the device instruction covers the whole double range).  Both are refined by the same two Newton steps.
+// Fixed-step kernels do not use it and must match the oracle bit for bit, adaptive kernels are held to the same
+// bar as on the GPU (identical step counts, states within tolerance).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+// sde_rcp_fast's one inline-PTX statement, `asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));`, becomes the
+// assignment below (r and x are the names in scope there; no other asm statement exists in the included headers)
+#define asm(...) (r = 1.0 / x)
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __constant__
+#define __shared__
+#define __restrict__
+#define __align__(n) __attribute__((aligned(n)))
+struct double2 { double x, y; };
+struct EmulDim { unsigned x = 0, y = 0, z = 0; };
+static thread_local EmulDim threadIdx, blockIdx;
+static thread_local EmulDim blockDim, gridDim;
+
+static inline int __double2hiint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) {
+  int64_t b = (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo); double x; std::memcpy(&x, &b, 8); return x;
+}
+static inline double __longlong_as_double(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
+static inline float __int_as_float(int v) { float x; std::memcpy(&x, &v, 4); return x; }
+static inline int __float_as_int(float v) { int x; std::memcpy(&x, &v, 4); return x; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+// single-lane warp
+static inline int __any_sync(unsigned, int p) { return p != 0; }
+static inline int __all_sync(unsigned, int p) { return p != 0; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template <class V> static inline V __shfl_sync(unsigned, V v, int, int = 32) { return v; }
+static inline void __syncthreads() {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+template <class V> static inline V atomicAdd(V* p, V v) { V old = *p; *p = old + v; return old; }
+using std::fma;
+using std::fabs;
+using std::sqrt;
+
+#include "../simplediffeq.jl_b200/csrc/device/sde_kernels.cuh"
+#include "../simplediffeq.jl_b200/csrc/device/sde_systems.cuh"
+
+alignas(16) unsigned char sde_dyn_smem[16];   // the staged writer's dynamic shared memory (not emulated)
+
+namespace {
+
+struct Call {
+  int alg, save, compat, layout;
+  long long n_traj, n_steps, n_save, n_out, max_attempts;
+  double t0, tf, dt, abstol, reltol;
+  const void *u0, *p, *tgrid, *saveat;
+  void *out_u, *out_t;
+  int *naccept, *nreject, *retcode;
+};
+
+template <class T>
+sde::KArgs<T> make_args(const Call& c, sde::u64* queue) {
+  sde::KArgs<T> a;
+  std::memset(&a, 0, sizeof a);
+  a.u0 = (const T*)c.u0; a.p = (const T*)c.p;
+  a.n_traj = c.n_traj; a.ld_in = c.n_traj;
+  a.t0 = (T)c.t0; a.tf = (T)c.tf; a.dt = (T)c.dt; a.abstol = (T)c.abstol; a.reltol = (T)c.reltol;
+  a.n_steps = c.n_steps; a.tgrid = (const T*)c.tgrid; a.saveat = (const T*)c.saveat; a.n_save = (int)c.n_save;
+  a.compat = c.compat & 3;           // like the launcher: bit 30 reaches the kernel as 0
+  a.layout = c.layout; a.max_attempts = c.max_attempts;
+  a.out_u = (T*)c.out_u; a.ld_out = c.n_traj; a.n_out = c.n_out; a.out_t = (T*)c.out_t;
+  a.naccept = c.naccept; a.nreject = c.nreject; a.retcode = c.retcode;
+  a.queue = queue;
+  return a;
+}
+
+// fixed step: the grid is one thread per trajectory
+template <class Sys, class T, class M, int SAVE>
+void run_fixed(const Call& c) {
+  sde::KArgs<T> a = make_args<T>(c, nullptr);
+  blockDim.x = 1; gridDim.x = (unsigned)c.n_traj;
+  for (long long i = 0; i < c.n_traj; ++i) {
+    blockIdx.x = (unsigned)i; threadIdx.x = 0;
+    sde::fixed_body<Sys, T, M, SAVE, false, false>(a);
+  }
+}
+
+// adaptive: one persistent thread drains the whole work queue
+template <class Sys, class T, class M, int SAVE, bool V9>
+void run_adaptive(const Call& c) {
+  sde::u64 queue[2] = {0, 0};
+  sde::KArgs<T> a = make_args<T>(c, queue);
+  blockDim.x = 1; gridDim.x = 1; blockIdx.x = 0; threadIdx.x = 0;
+  if (c.compat & 2) sde::adaptive_body<Sys, T, M, SAVE, V9, true>(a);
+  else sde::adaptive_body<Sys, T, M, SAVE, V9, false>(a);
+}
+
+template <class Sys, class T>
+int dispatch_alg(const Call& c) {
+  using namespace sde;
+  using TS = Tsit5Method<Sys, T>; using RK = RK4Method<Sys, T>; using EU = EulerMethod<Sys, T>;
+  using V7 = Vern7Method<Sys, T>; using V9 = Vern9Method<Sys, T>;
+#define FIX(M) do { if (c.save == kSaveEndpoint) run_fixed<Sys, T, M, kSaveEndpoint>(c); \
+                    else if (c.save == kSaveEveryStep) run_fixed<Sys, T, M, kSaveEveryStep>(c); else return -4; return 0; } while (0)
+#define ADA(M, V) do { if (c.save == kSaveEndpoint) run_adaptive<Sys, T, M, kSaveEndpoint, V>(c); \
+                       else if (c.save == kSaveAt) run_adaptive<Sys, T, M, kSaveAt, V>(c); \
+                       else run_adaptive<Sys, T, M, kSaveEveryStep, V>(c); return 0; } while (0)
+  switch (c.alg) {
+    case kTsit5: FIX(TS);
+    case kRK4: FIX(RK);
+    case kEuler: FIX(EU);
+    case kVern7: FIX(V7);
+    case kVern9: FIX(V9);
+    case kATsit5: ADA(TS, false);
+    case kAVern7: ADA(V7, false);
+    case kAVern9: ADA(V9, true);
+  }
+#undef FIX
+#undef ADA
+  return -1;
+}
+
+template <class T>
+int dispatch_sys(int sys, const Call& c) {
+  switch (sys) {
+    case 0: return dispatch_alg<sde::Lorenz, T>(c);
+    case 1: return dispatch_alg<sde::VanDerPol, T>(c);
+    case 2: return dispatch_alg<sde::Robertson, T>(c);
+    case 4: return dispatch_alg<sde::LinearDecay, T>(c);
+    case 5: return dispatch_alg<sde::ScalarGrowth, T>(c);
+    case 6: return dispatch_alg<sde::NonAutonomous, T>(c);
+  }
+  return -1;   // (3 = nbody: left out to keep this translation unit small; its kernels are covered on the GPU)
+}
+
+}  // namespace
+
+// sys: index into the library's registry order (lorenz, vanderpol, robertson, nbody, lineardecay, scalargrowth,
+// nonautonomous); the other arguments are the fields of sde::KArgs / sde_options_t with the same meaning.
+// Fixed-step saveat is not offered here: its schedule is built by the launcher (sde_api.cu), not by the kernel.
+extern "C" int emul_solve(int sys, int alg, int dtype, int save, int layout, int compat, long long n_traj,
+                          const void* u0, const void* p, double t0, double tf, double dt, double abstol, double reltol,
+                          long long n_steps, const void* tgrid, const void* saveat, long long n_save, long long n_out,
+                          long long max_attempts, void* out_u, void* out_t, int* naccept, int* nreject, int* retcode) {
+  Call c{alg, save, compat, layout, n_traj, n_steps, n_save, n_out, max_attempts, t0, tf, dt, abstol, reltol,
+         u0, p, tgrid, saveat, out_u, out_t, naccept, nreject, retcode};
+  return dtype == 0 ? dispatch_sys<double>(sys, c) : dispatch_sys<float>(sys, c);
+}

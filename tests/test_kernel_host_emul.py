@@ -1,0 +1,230 @@
+"""The DEVICE kernel source (csrc/device/sde_kernels.cuh: fixed_body / adaptive_body, generated stage code,
+tableaus, built-in systems) compiled for the host and run against the oracle -- without a GPU.
+
+tests/kernel_host_emul.cpp emulates one lane per warp and one thread per block (see its header for what that
+does and does not cover); this file drives it.  TEST INFRASTRUCTURE ONLY: the product has no CPU path, these
+tests exist so that the CPU tier of the suite (the one every round runs) already exercises the kernels' logic:
+stage arithmetic and FMA placement, Q1 / Q3 time quirks, every-step output in both layouts, the per-lane work
+queue, the log2-domain and the literal step controllers, the late accept branch, dtmin / maxiters exits,
+adaptive saveat and every-step output.  Bars = the GPU tests' bars (tests/test_gpu_parity.py).
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common as C
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DEV = os.path.join(ROOT, "simplediffeq.jl_b200", "csrc", "device")
+SRC = os.path.join(HERE, "kernel_host_emul.cpp")
+OUT_DIR = os.path.join(HERE, "_build")
+SYS_ID = dict(lorenz=0, vanderpol=1, robertson=2, lineardecay=4, scalargrowth=5, nonautonomous=6)
+ALG_ID = dict(GPUSimpleTsit5=0, GPUSimpleATsit5=1, GPUSimpleRK4=2, GPUSimpleVern7=3, GPUSimpleAVern7=4,
+              GPUSimpleVern9=5, GPUSimpleAVern9=6, GPUSimpleEuler=7)
+FIXED = ["GPUSimpleTsit5", "GPUSimpleRK4", "GPUSimpleVern7", "GPUSimpleVern9", "GPUSimpleEuler"]
+ADAPT = ["GPUSimpleATsit5", "GPUSimpleAVern7", "GPUSimpleAVern9"]
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """g++ -O2 -mfma -ffp-contract=off (only the explicit fma() calls fuse, like -fmad=false on the device);
+    rebuilt when the harness or any device header changes."""
+    files = [SRC] + sorted(os.path.join(DEV, f) for f in os.listdir(DEV) if f.endswith(".cuh"))
+    h = hashlib.sha256()
+    for f in files:
+        h.update(open(f, "rb").read())
+    os.makedirs(OUT_DIR, exist_ok=True)
+    lib = os.path.join(OUT_DIR, "libkernel_emul_%s.so" % h.hexdigest()[:16])
+    if not os.path.exists(lib):
+        for old in os.listdir(OUT_DIR):
+            if old.startswith("libkernel_emul_"):
+                os.remove(os.path.join(OUT_DIR, old))
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", lib])
+    L = ctypes.CDLL(lib)
+    vp, ll, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double
+    L.emul_solve.restype = ctypes.c_int
+    L.emul_solve.argtypes = [ctypes.c_int] * 6 + [ll, vp, vp, d, d, d, d, d, ll, vp, vp, ll, ll, ll, vp, vp, vp, vp, vp]
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _run(L, system, algname, u0, p, tspan, dt, *, save=0, layout=0, compat=0, abstol=1e-6, reltol=1e-3, tgrid=None,
+         saveat=None, n_out=1, max_attempts=0):
+    """u0 [n, N], p [n, NP] (rows = trajectories, like the oracle wrapper).  Returns a dict of outputs."""
+    dtype = u0.dtype
+    n, N = u0.shape
+    u0s, ps = np.ascontiguousarray(u0.T), np.ascontiguousarray(p.T)
+    n_steps = len(tgrid) - 1 if tgrid is not None else 0
+    n_save = len(saveat) if saveat is not None else 0
+    if save == 0:
+        out_u = np.full((N, n), np.nan, dtype=dtype)
+    elif layout == 0:
+        out_u = np.full((n, n_out, N), np.nan, dtype=dtype)
+    else:
+        out_u = np.full((n_out, N, n), np.nan, dtype=dtype)
+    adaptive = algname in ADAPT
+    if adaptive and save == 2:
+        out_t = np.full((n, n_out) if layout == 0 else (n_out, n), np.nan, dtype=dtype)
+    else:
+        out_t = np.full(n, np.nan, dtype=dtype)
+    nacc, nrej, ret = (np.full(n, -1, dtype=np.int32) for _ in range(3))
+    tg = None if tgrid is None else np.ascontiguousarray(tgrid, dtype=dtype)
+    sa = None if saveat is None else np.ascontiguousarray(saveat, dtype=dtype)
+    rc = L.emul_solve(SYS_ID[system], ALG_ID[algname], 0 if dtype == np.float64 else 1, save, layout, compat, n,
+                      _ptr(u0s), _ptr(ps), float(tspan[0]), float(tspan[1]), float(dt), float(abstol), float(reltol),
+                      n_steps, _ptr(tg), _ptr(sa), n_save, n_out, max_attempts, _ptr(out_u), _ptr(out_t),
+                      _ptr(nacc), _ptr(nrej), _ptr(ret))
+    assert rc == 0
+    return dict(u=out_u, t=out_t, naccept=nacc, nreject=nrej, retcode=ret)
+
+
+def _grid(sde, tspan, dt, dtype):
+    T = np.dtype(dtype).type
+    return sde.jl_range(T(tspan[0]), T(dt), T(tspan[1]), T)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algname", FIXED)
+@pytest.mark.parametrize("system", list(SYS_ID))
+def test_fixed_step_device_source_is_bit_identical_to_the_oracle(emul, sde, oracle, system, algname, dtype):
+    n = 37
+    u0, p = C.random_problem(system, n, dtype, seed=11)
+    tspan, dt = (0.25, 1.25), 0.03          # dt does not divide the span: the last step ends before tf (quirk Q5)
+    tg = _grid(sde, tspan, dt, dtype)
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg,
+                     save_mode=oracle.SAVE_EVERYSTEP, n_threads=4)
+    end = _run(emul, system, algname, u0, p, tspan, dt, tgrid=tg)
+    assert C.bits_equal(np.ascontiguousarray(end["u"].T), np.ascontiguousarray(o.u[:, -1, :]))
+    assert np.all(end["naccept"] == -1)      # fixed-step kernels do not touch the statistics (the launcher zeroes them)
+    slots = len(tg)
+    tm = _run(emul, system, algname, u0, p, tspan, dt, tgrid=tg, save=2, layout=0, n_out=slots)
+    soa = _run(emul, system, algname, u0, p, tspan, dt, tgrid=tg, save=2, layout=1, n_out=slots)
+    assert C.bits_equal(tm["u"], o.u), "max ulp diff %d" % C.max_ulp_diff(tm["u"], o.u)
+    assert C.bits_equal(np.ascontiguousarray(soa["u"].transpose(2, 0, 1)), o.u)
+
+
+# last field: fraction of trajectories whose step counts must be identical.  AVern9's 9th-order error estimate is
+# rounding noise at tight tolerances, so two pow implementations already disagree on a few.
+SWEEPS = [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8, 1.0), ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6, 1.0),
+          ("lorenz", "GPUSimpleAVern7", (0.0, 10.0), 1e-10, 1.0), ("lorenz", "GPUSimpleAVern9", (0.0, 4.0), 1e-9, 0.9)]
+
+
+@pytest.mark.parametrize("compat", [0, 2])       # log2-domain controller / literal pow-div-sqrt controller
+@pytest.mark.parametrize("system,algname,tspan,tol,same_frac", SWEEPS)
+def test_adaptive_device_source_reproduces_the_oracle_step_sequence(emul, oracle, system, algname, tspan, tol, same_frac,
+                                                                    compat):
+    """BASELINE configs 1 / 3 (and the Verner methods) at test size: identical accepted AND rejected step counts,
+    final state within 10 tolerance units -- through the per-lane work queue (one emulated lane drains all
+    trajectories) and the late accept branch."""
+    n = 96
+    u0, p = (C.lorenz_sweep(n) if system == "lorenz" else C.vdp_sweep(n, shuffled=True))
+    dt0 = float(np.float32(0.1))
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=tol, reltol=tol, want_t=True,
+                     n_threads=4)
+    g = _run(emul, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, compat=compat)
+    assert np.all(g["retcode"] == 0)
+    same = np.mean((g["naccept"] == o.naccept) & (g["nreject"] == o.nreject))
+    assert same >= same_frac, same
+    assert g["nreject"].sum() > 0                                   # the reject path was exercised
+    ou = o.u[:, 0, :]
+    err = np.abs(g["u"].T - ou) / (tol + tol * np.abs(ou))
+    assert err.max() <= 10.0, err.max()
+    assert C.bits_equal(g["t"], o.t[:, 0].astype(g["t"].dtype))     # final time: tf exactly (snap) on every trajectory
+
+
+def test_adaptive_saveat_and_everystep_device_source(emul, oracle):
+    n = 48
+    u0, p = C.lorenz_sweep(n)
+    dt0, tol = float(np.float32(0.1)), 1e-7
+    sa = np.array([0.0, 0.3, 0.31, 0.32, 1.0, 1.999, 2.0, 2.5])     # last point beyond tf: never reached (NaN)
+    o = oracle.solve("lorenz", "ATsit5", u0, p, 0.0, 2.0, dt0, abstol=tol, reltol=tol, saveat=sa, n_threads=4)
+    for layout in (0, 1):
+        g = _run(emul, "lorenz", "GPUSimpleATsit5", u0, p, (0.0, 2.0), dt0, abstol=tol, reltol=tol, save=1, layout=layout,
+                 saveat=sa, n_out=len(sa))
+        u = g["u"] if layout == 0 else np.ascontiguousarray(g["u"].transpose(2, 0, 1))
+        assert np.array_equal(g["naccept"], o.naccept)
+        assert np.all(np.isnan(u[:, -1, :])) and not np.any(np.isnan(u[:, :-1, :]))
+        err = np.abs(u[:, :-1] - o.u[:, :-1]) / (tol + tol * np.abs(o.u[:, :-1]))
+        assert err.max() <= 10.0
+        assert C.bits_equal(np.ascontiguousarray(u[:, 0, :]), u0)    # us[1] = u0 because saveat[1] == tspan[1] (quirk Q8)
+    cap = 256
+    oe = oracle.solve("lorenz", "ATsit5", u0, p, 0.0, 2.0, dt0, abstol=tol, reltol=tol, save_mode=oracle.SAVE_EVERYSTEP,
+                      max_out=cap, want_t=True, n_threads=4)
+    ge = _run(emul, "lorenz", "GPUSimpleATsit5", u0, p, (0.0, 2.0), dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=cap)
+    assert np.array_equal(ge["naccept"], oe.naccept) and np.all(ge["retcode"] == 0)
+    for i in (0, n // 2, n - 1):
+        k = int(oe.n[i])
+        assert k == ge["naccept"][i] + 1
+        assert np.allclose(ge["t"][i, :k], oe.t[i, :k], rtol=1e-9, atol=0)
+        assert np.all(np.abs(ge["u"][i, :k] - oe.u[i, :k]) <= 10 * tol * (1 + np.abs(oe.u[i, :k])))
+        assert np.all(np.isnan(ge["u"][i, k:]))                      # unused capacity
+    # a row that is too short: the first `cap` states are kept, naccept still counts all, retcode OUTPUT_FULL
+    small = _run(emul, "lorenz", "GPUSimpleATsit5", u0, p, (0.0, 2.0), dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=5)
+    assert np.array_equal(small["naccept"], oe.naccept) and np.all(small["retcode"] == 3)
+    assert C.bits_equal(small["u"], ge["u"][:, :5, :])
+
+
+def test_adaptive_failure_exits_device_source(emul, oracle):
+    # dt < dtmin: the reference throws error("dt<dtmin"); retcode 1 here (oracle: the same trajectory, same counts)
+    u0 = np.ones((3, 1)); p = np.array([[-1e17], [1.01], [-1e17]])
+    o = oracle.solve("scalargrowth", "ATsit5", u0, p, 0.0, 1.0, 1e-3, abstol=1e-10, reltol=1e-10, n_threads=1)
+    g = _run(emul, "scalargrowth", "GPUSimpleATsit5", u0, p, (0.0, 1.0), 1e-3, abstol=1e-10, reltol=1e-10)
+    assert list(g["retcode"]) == [1, 0, 1] and np.array_equal(g["retcode"], o.retcode)
+    assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    # maxiters: attempts (accepted + rejected) are capped, retcode 2, the time reached is reported
+    n = 16
+    u0, p = C.lorenz_sweep(n)
+    dt0 = float(np.float32(0.1))
+    limit = int(np.median(oracle.solve("lorenz", "ATsit5", u0, p, 0.0, 3.0, dt0, abstol=1e-8, reltol=1e-8,
+                                       n_threads=1).naccept))          # about half of the trajectories need more
+    o = oracle.solve("lorenz", "ATsit5", u0, p, 0.0, 3.0, dt0, abstol=1e-8, reltol=1e-8, max_attempts=limit, want_t=True,
+                     n_threads=1)
+    g = _run(emul, "lorenz", "GPUSimpleATsit5", u0, p, (0.0, 3.0), dt0, abstol=1e-8, reltol=1e-8, max_attempts=limit)
+    assert np.array_equal(g["retcode"], o.retcode) and set(g["retcode"]) == {0, 2}
+    hit = g["retcode"] == 2
+    assert np.all(g["naccept"][hit] + g["nreject"][hit] == limit)
+    assert np.all(g["t"][hit] < 3.0) and np.all(g["t"][~hit] == 3.0)
+    assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    # a NaN estimate is accepted and ends the solve with a NaN state and no error (quirk Q12)
+    u0n = np.array([[np.nan, 0.0, 0.0]]); pn = np.array([[10.0, 28.0, 8 / 3]])
+    o = oracle.solve("lorenz", "ATsit5", u0n, pn, 0.0, 1.0, dt0, abstol=1e-8, reltol=1e-8, n_threads=1)
+    g = _run(emul, "lorenz", "GPUSimpleATsit5", u0n, pn, (0.0, 1.0), dt0, abstol=1e-8, reltol=1e-8)
+    assert g["retcode"][0] == 0 and np.all(np.isnan(g["u"])) and np.all(np.isnan(o.u))
+    assert g["naccept"][0] == o.naccept[0] and g["nreject"][0] == o.nreject[0] == 0
+
+
+# ---- device source vs the reference's OWN SOURCE TEXT (the jlmini fixtures), no oracle in between ----------------
+import jlmini_cases as J  # noqa: E402
+
+_JFIXED = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH)
+           if c["alg"] not in J.ADAPTIVE and "saveat" not in c["kw"] and "error" not in c and c["system"] in SYS_ID]
+
+
+@pytest.mark.parametrize("case", _JFIXED, ids=[c["name"] for c in _JFIXED])
+def test_fixed_step_device_source_vs_reference_source_execution(emul, sde, case):
+    """Every fixed-step endpoint / every-step case of the two reference-source fixtures: the device kernels (host
+    emulation) must reproduce the states the reference's own `solve` text produced, bit for bit."""
+    a = J.case_inputs(case)
+    dtype = a["dtype"]
+    exp_t, exp_u = J.expected(case)
+    tg = sde.jl_range(a["t0"], a["dt"], a["tf"], dtype)
+    u0, p = a["u0"][None, :], a["p"][None, :]
+    tspan = (float(a["t0"]), float(a["tf"]))
+    if a["kind"] == "endpoint":
+        g = _run(emul, case["system"], case["alg"], u0, p, tspan, float(a["dt"]), tgrid=tg)
+        got = np.ascontiguousarray(g["u"].T)
+        want = np.ascontiguousarray(exp_u[-1:])
+    else:
+        g = _run(emul, case["system"], case["alg"], u0, p, tspan, float(a["dt"]), tgrid=tg, save=2, layout=0, n_out=len(tg))
+        got, want = g["u"][0], exp_u
+        assert len(tg) == case["n_out"]
+    canon = lambda x: np.where(np.isnan(x), np.nan, x)      # NaN payloads are not part of the contract
+    assert C.bits_equal(canon(got), canon(want)), "max ulp diff %d" % C.max_ulp_diff(got, want)
