@@ -56,8 +56,11 @@ using std::fma;
 using std::fabs;
 using std::sqrt;
 
+#include <vector>
+
 #include "../simplediffeq.jl_b200/csrc/device/sde_kernels.cuh"
 #include "../simplediffeq.jl_b200/csrc/device/sde_systems.cuh"
+#include "../simplediffeq.jl_b200/csrc/sde_interp_host_gen.h"   // the launcher's dense-output polynomial tables
 
 alignas(16) unsigned char sde_dyn_smem[16];   // the staged writer's dynamic shared memory (not emulated)
 
@@ -88,14 +91,55 @@ sde::KArgs<T> make_args(const Call& c, sde::u64* queue) {
   return a;
 }
 
+// The fixed-step save schedule is built on the host by the launcher (sde_api.cu: build_save_plan) and handed to the
+// kernel as plan_step / plan_b.  Restated here with the same operations (t = tgrid[s-1] + dt; theta = (savet -
+// (t - dt)) / dt; b_j(theta) by fma-Horner over the SAME tables, sde_interp_host_gen.h) so that the kernel's side --
+// the save loop, dense_prepare (extra stages, quirks Q2 / Q3) and dense_combine -- can be run here.
+template <class T>
+void build_plan(int alg, const T* tgrid, long long n_steps, T t0, T dt, const T* saveat, long long n_save,
+                std::vector<int>* step, std::vector<T>* b) {
+  const double* poly; const int* len; int nb, deg;
+  if (alg == sde::kTsit5) { poly = &sde_host::kTsit5Poly[0][0]; len = sde_host::kTsit5Len; nb = sde_host::kTsit5NB; deg = sde_host::kTsit5Deg; }
+  else if (alg == sde::kVern7) { poly = &sde_host::kVern7Poly[0][0]; len = sde_host::kVern7Len; nb = sde_host::kVern7NB; deg = sde_host::kVern7Deg; }
+  else { poly = &sde_host::kVern9Poly[0][0]; len = sde_host::kVern9Len; nb = sde_host::kVern9NB; deg = sde_host::kVern9Deg; }
+  step->assign((size_t)n_save, (int)(n_steps + 1));      // "never reached"
+  b->assign((size_t)n_save * nb, (T)0);
+  long long cur = 0;
+  if (n_save > 0 && t0 == saveat[0]) { (*step)[0] = 0; cur = 1; }
+  for (long long s = 1; s <= n_steps && cur < n_save; ++s) {
+    volatile T tv = tgrid[s - 1];
+    tv = tv + dt;
+    const T t = tv;
+    while (cur < n_save && saveat[cur] <= t) {
+      volatile T tm = t - dt;
+      const T th = (saveat[cur] - tm) / dt;
+      for (int j = 0; j < nb; ++j) {
+        const double* c = poly + (size_t)j * deg;
+        T acc = (T)c[len[j] - 1];
+        for (int d = len[j] - 2; d >= 0; --d) acc = std::fma(th, acc, (T)c[d]);
+        (*b)[(size_t)cur * nb + j] = acc;
+      }
+      (*step)[(size_t)cur] = (int)s;
+      ++cur;
+    }
+  }
+}
+
 // fixed step: the grid is one thread per trajectory
-template <class Sys, class T, class M, int SAVE>
+template <class Sys, class T, class M, int SAVE, bool Q2 = false>
 void run_fixed(const Call& c) {
   sde::KArgs<T> a = make_args<T>(c, nullptr);
+  std::vector<int> plan_step;
+  std::vector<T> plan_b;
+  if (SAVE == sde::kSaveAt) {
+    build_plan<T>(c.alg, (const T*)c.tgrid, c.n_steps, (T)c.t0, (T)c.dt, (const T*)c.saveat, c.n_save, &plan_step, &plan_b);
+    a.plan_step = plan_step.data();
+    a.plan_b = plan_b.data();
+  }
   blockDim.x = 1; gridDim.x = (unsigned)c.n_traj;
   for (long long i = 0; i < c.n_traj; ++i) {
     blockIdx.x = (unsigned)i; threadIdx.x = 0;
-    sde::fixed_body<Sys, T, M, SAVE, false, false>(a);
+    sde::fixed_body<Sys, T, M, SAVE, Q2, false>(a);
   }
 }
 
@@ -116,20 +160,26 @@ int dispatch_alg(const Call& c) {
   using V7 = Vern7Method<Sys, T>; using V9 = Vern9Method<Sys, T>;
 #define FIX(M) do { if (c.save == kSaveEndpoint) run_fixed<Sys, T, M, kSaveEndpoint>(c); \
                     else if (c.save == kSaveEveryStep) run_fixed<Sys, T, M, kSaveEveryStep>(c); else return -4; return 0; } while (0)
+#define FIXS(M) do { if (c.save == kSaveEndpoint) run_fixed<Sys, T, M, kSaveEndpoint>(c); \
+                     else if (c.save == kSaveEveryStep) run_fixed<Sys, T, M, kSaveEveryStep>(c); \
+                     else run_fixed<Sys, T, M, kSaveAt>(c); return 0; } while (0)
 #define ADA(M, V) do { if (c.save == kSaveEndpoint) run_adaptive<Sys, T, M, kSaveEndpoint, V>(c); \
                        else if (c.save == kSaveAt) run_adaptive<Sys, T, M, kSaveAt, V>(c); \
                        else run_adaptive<Sys, T, M, kSaveEveryStep, V>(c); return 0; } while (0)
   switch (c.alg) {
-    case kTsit5: FIX(TS);
+    case kTsit5: FIXS(TS);
     case kRK4: FIX(RK);
     case kEuler: FIX(EU);
-    case kVern7: FIX(V7);
-    case kVern9: FIX(V9);
+    case kVern7: FIXS(V7);
+    case kVern9:      // saveat: the reference's dense output (quirk Q2) unless SDE_COMPAT_FIX_VERN9_INTERP (bit 0)
+      if (c.save == kSaveAt) { if (c.compat & 1) run_fixed<Sys, T, V9, kSaveAt, false>(c); else run_fixed<Sys, T, V9, kSaveAt, true>(c); return 0; }
+      FIX(V9);
     case kATsit5: ADA(TS, false);
     case kAVern7: ADA(V7, false);
     case kAVern9: ADA(V9, true);
   }
 #undef FIX
+#undef FIXS
 #undef ADA
   return -1;
 }
@@ -151,7 +201,6 @@ int dispatch_sys(int sys, const Call& c) {
 
 // sys: index into the library's registry order (lorenz, vanderpol, robertson, nbody, lineardecay, scalargrowth,
 // nonautonomous); the other arguments are the fields of sde::KArgs / sde_options_t with the same meaning.
-// Fixed-step saveat is not offered here: its schedule is built by the launcher (sde_api.cu), not by the kernel.
 extern "C" int emul_solve(int sys, int alg, int dtype, int save, int layout, int compat, long long n_traj,
                           const void* u0, const void* p, double t0, double tf, double dt, double abstol, double reltol,
                           long long n_steps, const void* tgrid, const void* saveat, long long n_save, long long n_out,

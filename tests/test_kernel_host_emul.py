@@ -228,3 +228,43 @@ def test_fixed_step_device_source_vs_reference_source_execution(emul, sde, case)
         assert len(tg) == case["n_out"]
     canon = lambda x: np.where(np.isnan(x), np.nan, x)      # NaN payloads are not part of the contract
     assert C.bits_equal(canon(got), canon(want)), "max ulp diff %d" % C.max_ulp_diff(got, want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("compat", [0, 1])
+@pytest.mark.parametrize("algname", ["GPUSimpleTsit5", "GPUSimpleVern7", "GPUSimpleVern9"])
+@pytest.mark.parametrize("system", ["lorenz", "nonautonomous"])
+def test_fixed_saveat_device_source_is_bit_identical_to_the_oracle(emul, sde, oracle, system, algname, compat, dtype):
+    """The kernel side of fixed-step saveat (save loop, extra stages with the reference's time base -- quirk Q3 --,
+    Vern9's as-written dense output -- quirk Q2 -- or its corrected form, NaN for unreached points) on the CPU."""
+    if compat and algname != "GPUSimpleVern9":
+        pytest.skip("compat flag only affects Vern9")
+    n = 29
+    u0, p = C.random_problem(system, n, dtype, seed=3)
+    tspan, dt = (0.0, 1.0), 0.05
+    saveat = np.array([0.0, 0.01, 0.02, 0.05, 0.07, 0.33, 0.5, 0.999, 1.0, 1.2], dtype=dtype)
+    tg = _grid(sde, tspan, dt, dtype)
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg, saveat=saveat,
+                     compat=compat, n_threads=4)
+    for layout in (0, 1):
+        g = _run(emul, system, algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=layout, compat=compat, saveat=saveat,
+                 n_out=len(saveat))
+        u = g["u"] if layout == 0 else np.ascontiguousarray(g["u"].transpose(2, 0, 1))
+        assert C.bits_equal(u, o.u), "max ulp diff %d" % C.max_ulp_diff(u, o.u)
+        assert np.all(np.isnan(u[:, -1, :])) and not np.any(np.isnan(u[:, :-1, :]))
+
+
+_JSAVEAT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH)
+            if c["alg"] not in J.ADAPTIVE and "saveat" in c["kw"] and "error" not in c and c["system"] in SYS_ID]
+
+
+@pytest.mark.parametrize("case", _JSAVEAT, ids=[c["name"] for c in _JSAVEAT])
+def test_fixed_saveat_device_source_vs_reference_source_execution(emul, sde, case):
+    a = J.case_inputs(case)
+    dtype = a["dtype"]
+    _, exp_u = J.expected(case)
+    tg = sde.jl_range(a["t0"], a["dt"], a["tf"], dtype)
+    g = _run(emul, case["system"], case["alg"], a["u0"][None, :], a["p"][None, :], (float(a["t0"]), float(a["tf"])),
+             float(a["dt"]), tgrid=tg, save=1, layout=0, saveat=a["saveat"], n_out=len(a["saveat"]))
+    canon = lambda x: np.where(np.isnan(x), np.nan, x)
+    assert C.bits_equal(canon(g["u"][0]), canon(exp_u)), "max ulp diff %d" % C.max_ulp_diff(g["u"][0], exp_u)
