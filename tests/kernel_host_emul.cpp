@@ -58,8 +58,20 @@ using std::sqrt;
 
 #include <vector>
 
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
+// FP32 Box-Muller of the EM generator: CUDA's sincospif has no libm twin; the FP32 stream is only held to 3e-6
+static inline void sincospif(float x, float* s, float* c) {
+  const double a = 3.14159265358979323846 * (double)x;
+  *s = (float)std::sin(a); *c = (float)std::cos(a);
+}
+
 #include "../simplediffeq.jl_b200/csrc/device/sde_kernels.cuh"
 #include "../simplediffeq.jl_b200/csrc/device/sde_systems.cuh"
+// sde_em.cuh returns a pointer to a function-local __shared__ array (em_load_table): shared memory outlives the
+// call on the device, so it has to be static here (the kernel bodies above only use theirs locally)
+#undef __shared__
+#define __shared__ static
+#include "../simplediffeq.jl_b200/csrc/device/sde_em.cuh"
 #include "../simplediffeq.jl_b200/csrc/sde_interp_host_gen.h"   // the launcher's dense-output polynomial tables
 
 alignas(16) unsigned char sde_dyn_smem[16];   // the staged writer's dynamic shared memory (not emulated)
@@ -208,4 +220,60 @@ extern "C" int emul_solve(int sys, int alg, int dtype, int save, int layout, int
   Call c{alg, save, compat, layout, n_traj, n_steps, n_save, n_out, max_attempts, t0, tf, dt, abstol, reltol,
          u0, p, tgrid, saveat, out_u, out_t, naccept, nreject, retcode};
   return dtype == 0 ? dispatch_sys<double>(sys, c) : dispatch_sys<float>(sys, c);
+}
+
+// ---- SimpleEM (csrc/device/sde_em.cuh: em_body, Philox4x32-10 + Box-Muller) ---------------------------------------
+namespace {
+template <class Sys, class T>
+int run_em(int save, int noise_mode, const sde::EMArgs<T>& a) {
+  using namespace sde;
+  blockDim.x = 1; gridDim.x = (unsigned)a.n_traj;
+  for (long long i = 0; i < a.n_traj; ++i) {
+    blockIdx.x = (unsigned)i; threadIdx.x = 0;
+    if (save == kSaveEndpoint) {
+      if (noise_mode == kNoisePhilox) em_body<Sys, T, kSaveEndpoint, kNoisePhilox>(a);
+      else em_body<Sys, T, kSaveEndpoint, kNoiseProvided>(a);
+    } else {
+      if (noise_mode == kNoisePhilox) em_body<Sys, T, kSaveEveryStep, kNoisePhilox>(a);
+      else em_body<Sys, T, kSaveEveryStep, kNoiseProvided>(a);
+    }
+  }
+  return 0;
+}
+template <class T>
+int em_dispatch(int sys, int save, int layout, int noise_mode, long long n, const void* u0, const void* p, double t0,
+                double dt, long long n_steps, unsigned long long seed, long long traj_offset, const void* noise, void* out) {
+  sde::EMArgs<T> a;
+  std::memset(&a, 0, sizeof a);
+  a.u0 = (const T*)u0; a.p = (const T*)p; a.n_traj = n; a.ld_in = n; a.t0 = (T)t0; a.dt = (T)dt; a.n_steps = n_steps;
+  a.layout = layout; a.out_u = (T*)out; a.ld_out = n; a.seed = seed; a.traj_offset = traj_offset;
+  a.noise = (const T*)noise; a.noise_ld = n;
+  switch (sys) {      // registry order of the library: gbm, linadd1, linadd2, ou, nondiag2x4
+    case 0: return run_em<sde::EmGBM, T>(save, noise_mode, a);
+    case 1: return run_em<sde::EmLinAdd1, T>(save, noise_mode, a);
+    case 2: return run_em<sde::EmLinAdd2, T>(save, noise_mode, a);
+    case 3: return run_em<sde::EmOU, T>(save, noise_mode, a);
+    case 4: return run_em<sde::EmNonDiag2x4, T>(save, noise_mode, a);
+  }
+  return -1;
+}
+}  // namespace
+
+extern "C" int emul_em_solve(int sys, int dtype, int save, int layout, int noise_mode, long long n, const void* u0,
+                             const void* p, double t0, double dt, long long n_steps, unsigned long long seed,
+                             long long traj_offset, const void* noise, void* out) {
+  return dtype == 0 ? em_dispatch<double>(sys, save, layout, noise_mode, n, u0, p, t0, dt, n_steps, seed, traj_offset, noise, out)
+                    : em_dispatch<float>(sys, save, layout, noise_mode, n, u0, p, t0, dt, n_steps, seed, traj_offset, noise, out);
+}
+
+// the normals a Philox solve consumes: out[(step*M + m) * n_traj + traj]
+extern "C" int emul_em_noise(int dtype, unsigned long long seed, long long traj_offset, long long n_traj,
+                             long long n_normals, void* out) {
+  blockDim.x = 1; gridDim.x = (unsigned)n_traj;
+  for (long long i = 0; i < n_traj; ++i) {
+    blockIdx.x = (unsigned)i; threadIdx.x = 0;
+    if (dtype == 0) sde::em_noise_body<double>(seed, traj_offset, n_traj, n_normals, (double*)out, n_traj);
+    else sde::em_noise_body<float>(seed, traj_offset, n_traj, n_normals, (float*)out, n_traj);
+  }
+  return 0;
 }

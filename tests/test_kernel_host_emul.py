@@ -268,3 +268,91 @@ def test_fixed_saveat_device_source_vs_reference_source_execution(emul, sde, cas
              float(a["dt"]), tgrid=tg, save=1, layout=0, saveat=a["saveat"], n_out=len(a["saveat"]))
     canon = lambda x: np.where(np.isnan(x), np.nan, x)
     assert C.bits_equal(canon(g["u"][0]), canon(exp_u)), "max ulp diff %d" % C.max_ulp_diff(g["u"][0], exp_u)
+
+
+# ---- SimpleEM device source (csrc/device/sde_em.cuh) ---------------------------------------------------------------
+import jlmini_em_cases as JE  # noqa: E402
+
+EM_SYS = dict(gbm=0, linadd1=1, linadd2=2, ou=3, nondiag2x4=4)
+EM_PROBLEMS = {"gbm": ([1.0], [0.1, 0.2], 1), "linadd1": ([0.5], [2.0, 1.0], 1), "linadd2": ([0.1, 0.2], [2.0, 1.0], 2),
+               "ou": ([0.3], [1.5, 1.0, 0.4], 1), "nondiag2x4": ([1.0, 1.0], [1.01], 4)}
+
+
+def _em_lib(emul):
+    vp, ll, d, ull = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double, ctypes.c_ulonglong
+    emul.emul_em_solve.restype = ctypes.c_int
+    emul.emul_em_solve.argtypes = [ctypes.c_int] * 5 + [ll, vp, vp, d, d, ll, ull, ll, vp, vp]
+    emul.emul_em_noise.restype = ctypes.c_int
+    emul.emul_em_noise.argtypes = [ctypes.c_int, ull, ll, ll, ll, vp]
+    return emul
+
+
+def _em_run(L, system, u0s, ps, t0, dt, n_steps, *, save=2, layout=0, noise=None, seed=0, traj_offset=0):
+    """u0s [N, n], ps [NP, n] (SoA like the C ABI); noise [n_steps, M, n] or None (Philox)."""
+    dtype = u0s.dtype
+    N, n = u0s.shape
+    if save == 0:
+        out = np.full((N, n), np.nan, dtype=dtype)
+    else:
+        out = np.full((n, n_steps + 1, N) if layout == 0 else (n_steps + 1, N, n), np.nan, dtype=dtype)
+    z = None if noise is None else np.ascontiguousarray(noise, dtype=dtype)
+    rc = L.emul_em_solve(EM_SYS[system], 0 if dtype == np.float64 else 1, save, layout, 0 if noise is None else 1, n,
+                         _ptr(np.ascontiguousarray(u0s)), _ptr(np.ascontiguousarray(ps)), float(t0), float(dt), n_steps,
+                         seed, traj_offset, _ptr(z), _ptr(out))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("system", list(EM_SYS))
+def test_em_device_source_on_supplied_normals_is_bit_identical_to_the_oracle(emul, oracle, system, dtype):
+    L = _em_lib(emul)
+    n, steps, dt = 41, 24, 1 / 32
+    rng = np.random.default_rng(3)
+    u0, p, M = EM_PROBLEMS[system]
+    u0s = (np.array(u0)[:, None] * (1 + 0.2 * rng.uniform(-1, 1, (len(u0), n)))).astype(dtype)
+    ps = (np.array(p)[:, None] * (1 + 0.2 * rng.uniform(-1, 1, (len(p), n)))).astype(dtype)
+    z = rng.standard_normal((steps, M, n)).astype(dtype)
+    want = oracle.em_solve(system, u0s, ps, 0.25, dt, steps, z)                      # [n][steps+1][N]
+    assert C.bits_equal(_em_run(L, system, u0s, ps, 0.25, dt, steps, noise=z, layout=0), want)
+    assert C.bits_equal(np.ascontiguousarray(_em_run(L, system, u0s, ps, 0.25, dt, steps, noise=z, layout=1).transpose(2, 0, 1)), want)
+    assert C.bits_equal(np.ascontiguousarray(_em_run(L, system, u0s, ps, 0.25, dt, steps, noise=z, save=0).T),
+                        np.ascontiguousarray(want[:, -1, :]))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_em_philox_stream_of_the_device_source(emul, oracle, dtype):
+    """The generator the kernels carry (Philox4x32-10 counters, Box-Muller through the table-driven log2 / sincos) vs
+    the oracle's independent restatement of the noise specification with libm; counter layout: a trajectory's stream
+    depends on its GLOBAL index only (traj_offset), and a Philox solve consumes exactly the dumped stream."""
+    L = _em_lib(emul)
+    n, steps, M = 50, 33, 3
+    z = np.empty((steps * M, n), dtype=dtype)
+    assert L.emul_em_noise(0 if dtype == np.float64 else 1, 20261017, 12345, n, steps * M, _ptr(z)) == 0
+    want = oracle.em_normals(dtype, 20261017, 12345, n, steps, M).reshape(steps * M, n)
+    tol = 1e-13 if dtype == np.float64 else 3e-6
+    assert np.max(np.abs(z.astype(np.float64) - want.astype(np.float64))) < tol
+    shifted = np.empty((steps * M, 10), dtype=dtype)
+    L.emul_em_noise(0 if dtype == np.float64 else 1, 20261017, 12345 + 7, 10, steps * M, _ptr(shifted))
+    assert C.bits_equal(shifted, np.ascontiguousarray(z[:, 7:17]))
+    # a Philox-driven solve == the same solve fed the dumped stream
+    u0s = np.ones((1, n), dtype=dtype); ps = np.tile(np.array([[0.1], [0.2]], dtype=dtype), (1, n))
+    z1 = np.empty((steps, n), dtype=dtype)
+    L.emul_em_noise(0 if dtype == np.float64 else 1, 99, 0, n, steps, _ptr(z1))
+    a = _em_run(L, "gbm", u0s, ps, 0.0, 1 / 64, steps, seed=99)
+    b = _em_run(L, "gbm", u0s, ps, 0.0, 1 / 64, steps, noise=z1[:, None, :])
+    assert C.bits_equal(a, b)
+
+
+_JEM = [c for c in JE.load_cases() if "error" not in c]
+
+
+@pytest.mark.parametrize("case", _JEM, ids=[c["name"] for c in _JEM])
+def test_em_device_source_vs_reference_source_execution(emul, case):
+    """src/euler_maruyama.jl executed by jlmini (normals supplied) vs the device kernel source, bit for bit."""
+    L = _em_lib(emul)
+    T, u0, p, t0, tf, dt = JE.inputs(case)
+    exp_t, exp_u, z = JE.expected(case)
+    got = _em_run(L, case["system"], u0[:, None], p[:, None], t0, dt, case["n_out"] - 1,
+                  noise=z[:, :, None] if len(z) else np.zeros((0, u0.size, 1), dtype=T))
+    assert C.bits_equal(np.ascontiguousarray(got[0]), exp_u)
