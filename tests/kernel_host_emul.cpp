@@ -5,10 +5,16 @@
 // *** TEST INFRASTRUCTURE ONLY ***  Built and loaded by tests/test_kernel_host_emul.py; nothing in the product
 // links it and it is no CPU fallback: the library itself still fails with SDE_ERR_CUDA without a device.
 //
-// Emulation model: one thread per "warp" (lane 0 only), one thread per block.  The warp intrinsics degenerate
-// (ballot = bit 0, shuffle = identity, votes = the lane's own predicate), __shared__ arrays become locals and
-// atomicAdd a plain add, which is exact for a single thread.  The shared-memory STAGED writer needs 32 cooperating
-// lanes and is not emulated (it is covered on the GPU); everything else is.  The only arithmetic that differs
+// Emulation model, two modes (emul_set_lanes):
+//   1 lane : one thread per "warp" and per block; the warp intrinsics degenerate (ballot = bit 0, shuffle =
+//            identity, votes = the lane's own predicate).  Fast; used for most tests.
+//   32 lanes: one block = one warp of 32 host threads.  Every warp intrinsic the kernels use is called by all
+//            lanes of the warp at the same program point (the kernels keep those calls out of divergent code), so
+//            each one is a rendezvous: deposit the operand, barrier, read the others', barrier.  __shared__ arrays
+//            are shared by the block, atomicAdd is a real atomic.  This runs the warp-aggregated work queue
+//            (ballot / popc prefix / leader atomic / shuffle), the warp-vote exit and the shared-memory STAGED
+//            trajectory-major writer (half-warp flushes between __syncwarp()s) as 32 cooperating lanes.
+// Blocks run one after the other.  The only arithmetic that differs
 // from the device is the seed of sde_rcp_fast: MUFU.RCP64H there, the IEEE quotient 1.0 / x here (the float seed
 // that SDE_HOST_EMULATION selects in sde_common.cuh overflows for |x| > 3.4e38, which blown-up trajectories reach;
 // the device instruction covers the whole double range).  Both are refined by the same two Newton steps.
@@ -26,7 +32,11 @@
 #define __global__
 #define __forceinline__ inline
 #define __constant__
-#define __shared__
+#define __shared__ static      /* shared by the block's threads; blocks run one after the other */
+// The headers' one non-local shared declaration, `extern __shared__ __align__(16) unsigned char sde_dyn_smem[];`
+// (dynamic shared memory of the staged writer), cannot become `extern static`: the test fixture compiles against
+// copies of the device headers in which exactly that line reads EMUL_DYN_SMEM (nothing else is touched).
+#define EMUL_DYN_SMEM static __attribute__((aligned(16))) unsigned char sde_dyn_smem[65536];
 #define __restrict__
 #define __align__(n) __attribute__((aligned(n)))
 struct double2 { double x, y; };
@@ -44,18 +54,44 @@ static inline float __int_as_float(int v) { float x; std::memcpy(&x, &v, 4); ret
 static inline int __float_as_int(float v) { int x; std::memcpy(&x, &v, 4); return x; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-// single-lane warp
-static inline int __any_sync(unsigned, int p) { return p != 0; }
-static inline int __all_sync(unsigned, int p) { return p != 0; }
-static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
-template <class V> static inline V __shfl_sync(unsigned, V v, int, int = 32) { return v; }
-static inline void __syncthreads() {}
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
-template <class V> static inline V atomicAdd(V* p, V v) { V old = *p; *p = old + v; return old; }
+// ---- warp of g_lanes host threads (1 or 32) --------------------------------------------------------------------
+#include <pthread.h>
+static int g_lanes = 1;
+static pthread_barrier_t g_bar;
+static unsigned long long g_slot[32];
+static inline void warp_barrier() { if (g_lanes > 1) pthread_barrier_wait(&g_bar); }
+static inline unsigned __ballot_sync(unsigned, int p) {
+  if (g_lanes == 1) return p ? 1u : 0u;
+  g_slot[threadIdx.x & 31u] = p ? 1ull : 0ull;
+  warp_barrier();
+  unsigned b = 0;
+  for (int l = 0; l < g_lanes; ++l) b |= (unsigned)g_slot[l] << l;
+  warp_barrier();
+  return b;
+}
+static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0u; }
+static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, p) == (g_lanes == 1 ? 1u : 0xffffffffu); }
+template <class V> static inline V __shfl_sync(unsigned, V v, int src, int = 32) {
+  if (g_lanes == 1) return v;
+  static_assert(sizeof(V) <= 8, "shuffle operand");
+  unsigned long long raw = 0;
+  std::memcpy(&raw, &v, sizeof(V));
+  g_slot[threadIdx.x & 31u] = raw;
+  warp_barrier();
+  raw = g_slot[src & 31];
+  warp_barrier();
+  V out;
+  std::memcpy(&out, &raw, sizeof(V));
+  return out;
+}
+static inline void __syncthreads() { warp_barrier(); }      // one warp per block
+static inline void __syncwarp(unsigned = 0xffffffffu) { warp_barrier(); }
+template <class V> static inline V atomicAdd(V* p, V v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 using std::fma;
 using std::fabs;
 using std::sqrt;
 
+#include <thread>
 #include <vector>
 
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
@@ -65,16 +101,11 @@ static inline void sincospif(float x, float* s, float* c) {
   *s = (float)std::sin(a); *c = (float)std::cos(a);
 }
 
-#include "../simplediffeq.jl_b200/csrc/device/sde_kernels.cuh"
-#include "../simplediffeq.jl_b200/csrc/device/sde_systems.cuh"
-// sde_em.cuh returns a pointer to a function-local __shared__ array (em_load_table): shared memory outlives the
-// call on the device, so it has to be static here (the kernel bodies above only use theirs locally)
-#undef __shared__
-#define __shared__ static
-#include "../simplediffeq.jl_b200/csrc/device/sde_em.cuh"
-#include "../simplediffeq.jl_b200/csrc/sde_interp_host_gen.h"   // the launcher's dense-output polynomial tables
+#include "sde_kernels.cuh"        // copies of csrc/device/*.cuh made by the test fixture (see EMUL_DYN_SMEM below)
+#include "sde_systems.cuh"
+#include "sde_em.cuh"
+#include "sde_interp_host_gen.h"   // csrc/: the launcher's dense-output polynomial tables
 
-alignas(16) unsigned char sde_dyn_smem[16];   // the staged writer's dynamic shared memory (not emulated)
 
 namespace {
 
@@ -86,6 +117,25 @@ struct Call {
   void *out_u, *out_t;
   int *naccept, *nreject, *retcode;
 };
+
+// run `body` as n_blocks blocks of g_lanes threads, one block after the other
+template <class Body>
+void launch_blocks(long long n_blocks, Body body) {
+  for (long long b = 0; b < n_blocks; ++b) {
+    if (g_lanes == 1) {
+      blockDim.x = 1; gridDim.x = (unsigned)n_blocks; blockIdx.x = (unsigned)b; threadIdx.x = 0;
+      body();
+      continue;
+    }
+    std::vector<std::thread> lanes;
+    for (int l = 0; l < g_lanes; ++l)
+      lanes.emplace_back([=]() {
+        blockDim.x = (unsigned)g_lanes; gridDim.x = (unsigned)n_blocks; blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)l;
+        body();
+      });
+    for (auto& t : lanes) t.join();
+  }
+}
 
 template <class T>
 sde::KArgs<T> make_args(const Call& c, sde::u64* queue) {
@@ -148,11 +198,14 @@ void run_fixed(const Call& c) {
     a.plan_step = plan_step.data();
     a.plan_b = plan_b.data();
   }
-  blockDim.x = 1; gridDim.x = (unsigned)c.n_traj;
-  for (long long i = 0; i < c.n_traj; ++i) {
-    blockIdx.x = (unsigned)i; threadIdx.x = 0;
-    sde::fixed_body<Sys, T, M, SAVE, Q2, false>(a);
+  const long long n_blocks = (c.n_traj + g_lanes - 1) / g_lanes;
+  if constexpr (SAVE != sde::kSaveEndpoint) {
+    if (c.compat & 16) {      // emulation-only flag: the STAGED trajectory-major writer (needs the 32-lane mode)
+      launch_blocks(n_blocks, [&]() { sde::fixed_body<Sys, T, M, SAVE, Q2, true>(a); });
+      return;
+    }
   }
+  launch_blocks(n_blocks, [&]() { sde::fixed_body<Sys, T, M, SAVE, Q2, false>(a); });
 }
 
 // adaptive: one persistent thread drains the whole work queue
@@ -160,9 +213,9 @@ template <class Sys, class T, class M, int SAVE, bool V9>
 void run_adaptive(const Call& c) {
   sde::u64 queue[2] = {0, 0};
   sde::KArgs<T> a = make_args<T>(c, queue);
-  blockDim.x = 1; gridDim.x = 1; blockIdx.x = 0; threadIdx.x = 0;
-  if (c.compat & 2) sde::adaptive_body<Sys, T, M, SAVE, V9, true>(a);
-  else sde::adaptive_body<Sys, T, M, SAVE, V9, false>(a);
+  // persistent blocks: the first one drains the queue, the second finds it empty and leaves through the vote exit
+  if (c.compat & 2) launch_blocks(2, [&]() { sde::adaptive_body<Sys, T, M, SAVE, V9, true>(a); });
+  else launch_blocks(2, [&]() { sde::adaptive_body<Sys, T, M, SAVE, V9, false>(a); });
 }
 
 template <class Sys, class T>
@@ -227,9 +280,7 @@ namespace {
 template <class Sys, class T>
 int run_em(int save, int noise_mode, const sde::EMArgs<T>& a) {
   using namespace sde;
-  blockDim.x = 1; gridDim.x = (unsigned)a.n_traj;
-  for (long long i = 0; i < a.n_traj; ++i) {
-    blockIdx.x = (unsigned)i; threadIdx.x = 0;
+  launch_blocks((a.n_traj + g_lanes - 1) / g_lanes, [&]() {
     if (save == kSaveEndpoint) {
       if (noise_mode == kNoisePhilox) em_body<Sys, T, kSaveEndpoint, kNoisePhilox>(a);
       else em_body<Sys, T, kSaveEndpoint, kNoiseProvided>(a);
@@ -237,7 +288,7 @@ int run_em(int save, int noise_mode, const sde::EMArgs<T>& a) {
       if (noise_mode == kNoisePhilox) em_body<Sys, T, kSaveEveryStep, kNoisePhilox>(a);
       else em_body<Sys, T, kSaveEveryStep, kNoiseProvided>(a);
     }
-  }
+  });
   return 0;
 }
 template <class T>
@@ -269,11 +320,18 @@ extern "C" int emul_em_solve(int sys, int dtype, int save, int layout, int noise
 // the normals a Philox solve consumes: out[(step*M + m) * n_traj + traj]
 extern "C" int emul_em_noise(int dtype, unsigned long long seed, long long traj_offset, long long n_traj,
                              long long n_normals, void* out) {
-  blockDim.x = 1; gridDim.x = (unsigned)n_traj;
-  for (long long i = 0; i < n_traj; ++i) {
-    blockIdx.x = (unsigned)i; threadIdx.x = 0;
+  launch_blocks((n_traj + g_lanes - 1) / g_lanes, [&]() {
     if (dtype == 0) sde::em_noise_body<double>(seed, traj_offset, n_traj, n_normals, (double*)out, n_traj);
     else sde::em_noise_body<float>(seed, traj_offset, n_traj, n_normals, (float*)out, n_traj);
-  }
+  });
+  return 0;
+}
+
+// 1 = single-lane warps (default), 32 = full warps of 32 host threads (see the header of this file)
+extern "C" int emul_set_lanes(int lanes) {
+  if (lanes != 1 && lanes != 32) return -1;
+  if (g_lanes > 1) pthread_barrier_destroy(&g_bar);
+  g_lanes = lanes;
+  if (lanes > 1) pthread_barrier_init(&g_bar, nullptr, (unsigned)lanes);
   return 0;
 }

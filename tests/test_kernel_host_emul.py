@@ -32,7 +32,8 @@ ADAPT = ["GPUSimpleATsit5", "GPUSimpleAVern7", "GPUSimpleAVern9"]
 
 @pytest.fixture(scope="session")
 def emul():
-    """g++ -O2 -mfma -ffp-contract=off (only the explicit fma() calls fuse, like -fmad=false on the device);
+    """g++ -O1 -mfma -ffp-contract=off (only the explicit fma() calls fuse, like -fmad=false on the device; -O1 compiles
+    a third faster than -O2 and IEEE results do not depend on the level);
     rebuilt when the harness or any device header changes."""
     files = [SRC] + sorted(os.path.join(DEV, f) for f in os.listdir(DEV) if f.endswith(".cuh"))
     h = hashlib.sha256()
@@ -44,7 +45,19 @@ def emul():
         for old in os.listdir(OUT_DIR):
             if old.startswith("libkernel_emul_"):
                 os.remove(os.path.join(OUT_DIR, old))
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", lib])
+        # verbatim copies of the device headers, except the one `extern __shared__` declaration (see the harness)
+        inc = os.path.join(OUT_DIR, "device_headers")
+        os.makedirs(inc, exist_ok=True)
+        replaced = 0
+        for f in files[1:]:
+            text = open(f).read()
+            decl = "extern __shared__ __align__(16) unsigned char sde_dyn_smem[];"
+            replaced += text.count(decl)
+            with open(os.path.join(inc, os.path.basename(f)), "w") as fh:
+                fh.write(text.replace(decl, "EMUL_DYN_SMEM"))
+        assert replaced == 1
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                               "-I", inc, "-I", os.path.join(ROOT, "simplediffeq.jl_b200", "csrc"), SRC, "-o", lib])
     L = ctypes.CDLL(lib)
     vp, ll, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double
     L.emul_solve.restype = ctypes.c_int
@@ -356,3 +369,56 @@ def test_em_device_source_vs_reference_source_execution(emul, case):
     got = _em_run(L, case["system"], u0[:, None], p[:, None], t0, dt, case["n_out"] - 1,
                   noise=z[:, :, None] if len(z) else np.zeros((0, u0.size, 1), dtype=T))
     assert C.bits_equal(np.ascontiguousarray(got[0]), exp_u)
+
+
+# ---- full warps: 32 cooperating lanes (work queue aggregation, vote exit, shared-memory staged writer) -----------------
+@pytest.fixture()
+def warp32(emul):
+    emul.emul_set_lanes.argtypes = [ctypes.c_int]
+    assert emul.emul_set_lanes(32) == 0
+    yield emul
+    assert emul.emul_set_lanes(1) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algname", ["GPUSimpleTsit5", "GPUSimpleRK4", "GPUSimpleVern7"])
+def test_staged_trajectory_major_writer_with_32_lanes(warp32, sde, oracle, algname, dtype):
+    """The shared-memory staged series writer (every warp buffers S slots of its 32 trajectories, half-warps flush
+    contiguous runs) as 32 cooperating host threads: ragged last warp (n = 70), partial last flush, every-step and
+    saveat outputs -- bit-identical to the oracle."""
+    n = 70
+    u0, p = C.random_problem("lorenz", n, dtype, seed=21)
+    tspan, dt = (0.0, 1.0), 0.02
+    tg = _grid(sde, tspan, dt, dtype)
+    o = oracle.solve("lorenz", C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg,
+                     save_mode=oracle.SAVE_EVERYSTEP, n_threads=4)
+    g = _run(warp32, "lorenz", algname, u0, p, tspan, dt, tgrid=tg, save=2, layout=0, n_out=len(tg), compat=16)
+    assert C.bits_equal(g["u"], o.u), "max ulp diff %d" % C.max_ulp_diff(g["u"], o.u)
+    if algname != "GPUSimpleRK4":
+        saveat = np.linspace(0.0, 1.0, 38).astype(dtype)
+        os_ = oracle.solve("lorenz", C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg,
+                           saveat=saveat, n_threads=4)
+        gs = _run(warp32, "lorenz", algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=0, saveat=saveat,
+                  n_out=len(saveat), compat=16)
+        assert C.bits_equal(gs["u"], os_.u)
+
+
+@pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8),
+                                                      ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6),
+                                                      ("lorenz", "GPUSimpleAVern7", (0.0, 5.0), 1e-10)])
+def test_work_queue_with_32_lanes_equals_one_lane(warp32, emul, oracle, system, algname, tspan, tol):
+    """Per-lane work queue with warp-aggregated atomics (ballot, popc prefix, leader atomicAdd, shuffle) and the
+    warp-vote exit, 32 real lanes, unequal step counts (shuffled sweep), n not a multiple of 32: every trajectory
+    gets exactly the result the single-lane run gives (bit for bit) and the oracle's step counts."""
+    n = 150
+    u0, p = (C.lorenz_sweep(n) if system == "lorenz" else C.vdp_sweep(n, shuffled=True))
+    dt0 = float(np.float32(0.1))
+    g32 = _run(warp32, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol)
+    assert emul.emul_set_lanes(1) == 0
+    g1 = _run(emul, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol)
+    assert emul.emul_set_lanes(32) == 0
+    for k in ("u", "t", "naccept", "nreject", "retcode"):
+        assert C.bits_equal(g32[k], g1[k]), k
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=tol, reltol=tol, n_threads=4)
+    assert np.array_equal(g32["naccept"], o.naccept) and np.array_equal(g32["nreject"], o.nreject)
+    assert np.all(g32["retcode"] == 0)
