@@ -15,6 +15,7 @@ static inline double __hiloint2double(int hi, int lo) {
   int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; std::memcpy(&x, &b, 8); return x;
 }
 static inline double __longlong_as_double(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
+static inline long long __double_as_longlong(double x) { long long v; std::memcpy(&v, &x, 8); return v; }
 static inline float __int_as_float(int v) { float x; std::memcpy(&x, &v, 4); return x; }
 using std::fma;
 #include "../simplediffeq.jl_b200/csrc/device/sde_common.cuh"
@@ -30,6 +31,10 @@ double emul_jl_min(double a, double b) { return sde::jl_min(a, b); }
 void emul_sincos_halfpi(const double* v, double* sn, double* cs, long n) {
   for (long i = 0; i < n; ++i) sde::sde_sincos_halfpi(v[i], sde::k_ctrl, &sn[i], &cs[i]);
 }
+// y fixed, x varies: the controller's calls (EEst^beta1, qold^beta2)
+void emul_pow_glibc(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_pow_glibc(x[i], y); }
+// the C library's pow on the same arguments, called from the same process (no numpy / SIMD variant in between)
+void host_libm_pow(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y); }
 int emul_ctrl_count() { return sde::kC_count; }
 double emul_ctrl(int i) { return sde::k_ctrl[i]; }
 }

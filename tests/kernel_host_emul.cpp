@@ -50,6 +50,7 @@ static inline double __hiloint2double(int hi, int lo) {
   int64_t b = (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo); double x; std::memcpy(&x, &b, 8); return x;
 }
 static inline double __longlong_as_double(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
+static inline long long __double_as_longlong(double x) { long long v; std::memcpy(&v, &x, 8); return v; }
 static inline float __int_as_float(int v) { float x; std::memcpy(&x, &v, 4); return x; }
 static inline int __float_as_int(float v) { int x; std::memcpy(&x, &v, 4); return x; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -112,3 +112,62 @@ def test_short_nan_minmax_equal_julia_semantics(emul):
                 assert same(emul.emul_max_abs_nan2(a, b), emul.emul_jl_max(abs(a), abs(b))), (a, b)
             if not (math.isnan(b) and not math.isnan(a)):      # invariant of min_abs_nan1
                 assert same(emul.emul_min_abs_nan1(a, b), emul.emul_jl_min(abs(a), abs(b))), (a, b)
+
+
+def _pow_pair(emul, x, y):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a, b = np.empty_like(x), np.empty_like(x)
+    for fn, out in ((emul.emul_pow_glibc, a), (emul.host_libm_pow, b)):
+        fn(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(y), out.ctypes.data_as(ctypes.c_void_p),
+           ctypes.c_long(len(x)))
+    return a, b
+
+
+def _glibc_version():
+    try:
+        g = ctypes.CDLL(None).gnu_get_libc_version
+        g.restype = ctypes.c_char_p
+        return tuple(int(v) for v in g().decode().split(".")[:2])
+    except Exception:
+        return None
+
+
+needs_glibc_pow = pytest.mark.skipif(
+    _glibc_version() is None or _glibc_version() < (2, 28) or "fma" not in open("/proc/cpuinfo").read(),
+    reason="sde_pow_glibc restates the FMA variant of the table-driven pow of glibc >= 2.28")
+
+
+def test_glibc_pow_tables_are_current():
+    """sde_glibc_pow_tables_gen.cuh is what tools/gen_glibc_pow_tables.py reads out of this host's libm."""
+    if _glibc_version() is None or _glibc_version() < (2, 28):
+        pytest.skip("no glibc >= 2.28 here")
+    path = os.path.join(ROOT, "simplediffeq.jl_b200", "csrc", "device", "sde_glibc_pow_tables_gen.cuh")
+    before = open(path).read()
+    try:
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_glibc_pow_tables.py")],
+                              stdout=subprocess.DEVNULL)
+        assert open(path).read() == before
+    finally:
+        open(path, "w").write(before)
+
+
+@needs_glibc_pow
+@pytest.mark.parametrize("y", [7.0 / 50.0, 2.0 / 25.0, 0.5, 1.0 / 3.0, 2.5, -0.14, 1.0, 17.0])
+def test_strict_controller_pow_is_the_host_libm_pow_bit_for_bit(emul, y):
+    """The device header's sde_pow_glibc (compiled for the host: the same IEEE operations the GPU executes
+    under -fmad=false) against the C library the oracle is linked with, on the controller's domain: error
+    estimates from 1e-300 to 1e+300, dense around 1 (where the accept/reject decision and the |y log x| <
+    2^-54 shortcut live), qold's clamp value 1e-4, subnormals, and the special values."""
+    rng = np.random.default_rng(int(abs(y) * 1000) + 20261017)
+    x = np.concatenate([
+        10.0 ** rng.uniform(-300, 300, 150_000), 10.0 ** rng.uniform(-12, 4, 200_000),
+        rng.uniform(0.25, 4.0, 100_000), 1 + rng.uniform(-1e-6, 1e-6, 20_000),
+        1 + rng.uniform(-1e-15, 1e-15, 5_000), 2.0 ** np.arange(-1074, 1024).astype(np.float64),
+        rng.uniform(0, 1, 5_000) * 2.0 ** -1022,
+        np.array([1e-4, 1.0, np.nextafter(1.0, 0), np.nextafter(1.0, 2), 0.0, np.inf, np.nan, 5e-324,
+                  np.finfo(np.float64).max, np.finfo(np.float64).tiny])])
+    got, ref = _pow_pair(emul, x, y)
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), nan)
+    bad = np.flatnonzero(got[~nan].view(np.uint64) != ref[~nan].view(np.uint64))
+    assert bad.size == 0, (bad.size, x[~nan][bad[:5]], got[~nan][bad[:5]], ref[~nan][bad[:5]])

@@ -1,0 +1,66 @@
+"""GPU: the literal controller (SDE_COMPAT_STRICT_CONTROLLER) in FP64 reproduces the oracle BIT FOR BIT on the
+adaptive BASELINE sweeps -- accepted and rejected counts, final states and final times -- config 4 (AVern9,
+1e-12: the step sequence depends on the last bit of `EEst^beta1`) included.
+
+Why this can hold: the strict path's pow is sde_pow_glibc (csrc/device/sde_common.cuh), the operation
+sequence of the C library the oracle is linked against; every other operation of the attempt is IEEE
+(+ - * / sqrt fma) in the reference's order.  tests/test_ctrl_math.py pins sde_pow_glibc against the host libm,
+tests/test_kernel_host_emul.py runs the kernel source on the CPU against the oracle; this file is the same
+statement on the device.
+
+STATUS: written when the round's GPU minutes were spent -- the CPU side (both tests above) is green, the
+device side had not been run when this file was committed.  The file sorts last so that `-x` reaches
+every other GPU test first.
+
+The test is skipped when the host's libm is not the one the device function restates (checked directly: the
+header compiled for the host must equal `pow` on a sample), because then the ORACLE is a different function."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common as C
+from test_gpu_parity import SWEEPS, _gpu, _oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_libm_is_the_restated_one(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "libctrl_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-shared", "-fPIC",
+                           os.path.join(ROOT, "tests", "ctrl_host_emul.cpp"), "-o", out])
+    L = ctypes.CDLL(out)
+    rng = np.random.default_rng(5)
+    x = np.ascontiguousarray(np.concatenate([10.0 ** rng.uniform(-30, 10, 200_000), rng.uniform(0.5, 2.0, 200_000)]))
+    ok = True
+    for y in (7.0 / 50.0, 2.0 / 25.0):
+        a, b = np.empty_like(x), np.empty_like(x)
+        for fn, o in ((L.emul_pow_glibc, a), (L.host_libm_pow, b)):
+            fn(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(y), o.ctypes.data_as(ctypes.c_void_p),
+               ctypes.c_long(len(x)))
+        ok = ok and bool(np.array_equal(a.view(np.uint64), b.view(np.uint64)))
+    return ok
+
+
+@pytest.mark.parametrize("system,algname,tspan,tol,sensitive", SWEEPS)
+def test_strict_controller_fp64_is_the_oracle_bit_for_bit(sde, oracle, host_libm_is_the_restated_one,
+                                                          system, algname, tspan, tol, sensitive):
+    if not host_libm_is_the_restated_one:
+        pytest.skip("this host's libm pow is not the glibc >= 2.28 FMA variant that sde_pow_glibc restates")
+    n = 4096
+    u0, p = (C.lorenz_sweep(n) if system == "lorenz" else C.vdp_sweep(n))
+    dt0 = float(np.float32(0.1))
+    g = _gpu(sde, system, algname, u0, p, tspan, dt=dt0, abstol=tol, reltol=tol, save_mode=0,
+             compat=sde._lib.COMPAT_STRICT_CONTROLLER)
+    o = _oracle(sde, oracle, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, save_mode=0)
+    assert np.all(g["retcode"] == 0) and np.all(o.retcode == 0)
+    same_acc = float(np.mean(g["naccept"] == o.naccept))
+    same_rej = float(np.mean(g["nreject"] == o.nreject))
+    assert same_acc == 1.0 and same_rej == 1.0, (same_acc, same_rej)
+    assert C.bits_equal(g["u"].T, o.u[:, 0, :]), "max ulp diff %d" % C.max_ulp_diff(g["u"].T, o.u[:, 0, :])
+    assert C.bits_equal(g["t_final"], np.full(n, tspan[1]))
