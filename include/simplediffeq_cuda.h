@@ -102,7 +102,11 @@ enum {
                                       divisions and sqrt, src/tsit5/gpuatsit5.jl:276-292) instead of the
                                       default log2-domain evaluation of the same formulas (1 log2 + 1 exp2,
                                       ~1e-15 relative difference in the next dt; accept/reject unchanged
-                                      except within ~1e-15 of EEst = 1) */
+                                      except within ~1e-15 of EEst = 1).  Its pow / powf is the operation
+                                      sequence of glibc's (>= 2.28, FMA variant), i.e. of the libm a CPU run
+                                      on an x86-64 Linux host uses, so that step sequences that hang on the
+                                      last bit of `EEst^beta1` (AVern9 at 1e-12; every Float32 solve) can be
+                                      reproduced bit for bit (DESIGN.md sections 2 and 6) */
 };
 
 typedef struct sde_system_s* sde_system_t;

@@ -17,6 +17,7 @@ static inline double __hiloint2double(int hi, int lo) {
 static inline double __longlong_as_double(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
 static inline long long __double_as_longlong(double x) { long long v; std::memcpy(&v, &x, 8); return v; }
 static inline float __int_as_float(int v) { float x; std::memcpy(&x, &v, 4); return x; }
+static inline int __float_as_int(float v) { int x; std::memcpy(&x, &v, 4); return x; }
 using std::fma;
 #include "../simplediffeq.jl_b200/csrc/device/sde_common.cuh"
 
@@ -35,6 +36,8 @@ void emul_sincos_halfpi(const double* v, double* sn, double* cs, long n) {
 void emul_pow_glibc(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_pow_glibc(x[i], y); }
 // the C library's pow on the same arguments, called from the same process (no numpy / SIMD variant in between)
 void host_libm_pow(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y); }
+void emul_powf_glibc(const float* x, float y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_powf_glibc(x[i], y); }
+void host_libm_powf(const float* x, float y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y); }
 int emul_ctrl_count() { return sde::kC_count; }
 double emul_ctrl(int i) { return sde::k_ctrl[i]; }
 }

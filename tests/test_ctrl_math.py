@@ -171,3 +171,23 @@ def test_strict_controller_pow_is_the_host_libm_pow_bit_for_bit(emul, y):
     assert np.array_equal(np.isnan(got), nan)
     bad = np.flatnonzero(got[~nan].view(np.uint64) != ref[~nan].view(np.uint64))
     assert bad.size == 0, (bad.size, x[~nan][bad[:5]], got[~nan][bad[:5]], ref[~nan][bad[:5]])
+
+
+@needs_glibc_pow
+@pytest.mark.parametrize("y", [np.float32(7.0 / 50.0), np.float32(2.0 / 25.0), np.float32(0.5), np.float32(-1.75),
+                               np.float32(1.0), np.float32(3.0)])
+def test_strict_controller_powf_is_the_host_libm_powf_bit_for_bit(emul, y):
+    """Float32 twin: sde_powf_glibc against the C library's powf on every 97th Float32 bit pattern (44 M
+    values: all exponents, both signs, subnormals, inf, NaN) and a dense band around 1."""
+    bits = np.arange(0, 2 ** 32, 97, dtype=np.uint64).astype(np.uint32)
+    one = np.float32(1.0).view(np.uint32)
+    band = (np.arange(-200_000, 200_000, dtype=np.int64) + int(one)).astype(np.uint32)
+    x = np.ascontiguousarray(np.concatenate([bits, band]).view(np.float32))
+    a, b = np.empty_like(x), np.empty_like(x)
+    for fn, out in ((emul.emul_powf_glibc, a), (emul.host_libm_powf, b)):
+        fn(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(float(y)), out.ctypes.data_as(ctypes.c_void_p),
+           ctypes.c_long(len(x)))
+    nan = np.isnan(b)
+    assert np.array_equal(np.isnan(a), nan)
+    bad = np.flatnonzero(a[~nan].view(np.uint32) != b[~nan].view(np.uint32))
+    assert bad.size == 0, (bad.size, x[~nan][bad[:5]], a[~nan][bad[:5]], b[~nan][bad[:5]])

@@ -99,6 +99,10 @@ def _run(L, system, algname, u0, p, tspan, dt, *, save=0, layout=0, compat=0, ab
     return dict(u=out_u, t=out_t, naccept=nacc, nreject=nrej, retcode=ret)
 
 
+def _nan_canon(a):
+    return np.where(np.isnan(a), np.array(np.nan, dtype=a.dtype), a)
+
+
 def _grid(sde, tspan, dt, dtype):
     T = np.dtype(dtype).type
     return sde.jl_range(T(tspan[0]), T(dt), T(tspan[1]), T)
@@ -429,11 +433,13 @@ def test_work_queue_with_32_lanes_equals_one_lane(warp32, emul, oracle, system, 
                                                       ("lorenz", "GPUSimpleAVern7", (0.0, 10.0), 1e-10),
                                                       ("lorenz", "GPUSimpleAVern9", (0.0, 10.0), 1e-12)])
 def test_literal_controller_with_the_oracles_libm_is_bit_identical(emul, oracle, system, algname, tspan, tol):
-    """SDE_COMPAT_STRICT_CONTROLLER is the reference's controller as written (two pow calls, divisions, sqrt).  Compiled
-    for the host it uses the same libm pow as the oracle, and then the kernel reproduces the oracle BIT FOR BIT --
-    states, final times, accepted and rejected counts -- on all four BASELINE-style sweeps, config 4 (AVern9 at 1e-12)
-    included.  So the step-count disagreement that remains on the GPU for config 4 is exactly
-    the difference between CUDA's pow and glibc's pow, not a difference in the algorithm."""
+    """SDE_COMPAT_STRICT_CONTROLLER is the reference's controller as written (two pow calls, divisions, sqrt), with
+    sde_pow_glibc -- the operation sequence of the oracle's libm pow (tests/test_ctrl_math.py pins it against the host
+    libm bit for bit) -- as its pow.  The kernel source then reproduces the oracle BIT FOR BIT -- states, final times,
+    accepted and rejected counts -- on all four BASELINE-style sweeps, config 4 (AVern9 at 1e-12) included.  The device
+    executes the same IEEE operations (-fmad=false), so this is the statement tests/test_zz_gpu_strict_bitexact.py
+    makes on the GPU.  (With CUDA's own pow the GPU agreed with the oracle on only ~50 % of config 4's step counts:
+    DESIGN.md section 6.)"""
     n = 200
     u0, p = C.random_problem(system, n, np.float64, seed=123)        # random, partly chaotic problems
     dt0 = float(np.float32(0.1))
@@ -443,3 +449,24 @@ def test_literal_controller_with_the_oracles_libm_is_bit_identical(emul, oracle,
     assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
     assert C.bits_equal(np.ascontiguousarray(g["u"].T), np.ascontiguousarray(o.u[:, 0, :]))
     assert C.bits_equal(g["t"], np.ascontiguousarray(o.t[:, 0]))
+
+
+@pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-4),
+                                                      ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-3),
+                                                      ("lorenz", "GPUSimpleAVern7", (0.0, 5.0), 1e-5),
+                                                      ("lorenz", "GPUSimpleAVern9", (0.0, 5.0), 1e-5)])
+def test_literal_controller_fp32_is_bit_identical(emul, oracle, system, algname, tspan, tol):
+    """Float32 states: the literal controller's powf is sde_powf_glibc, the operation sequence of the oracle's libm
+    powf.  In Float32 the reference's `tf - t - dtold < 1e-14` snap never triggers, so the number of trailing
+    micro-steps depends on the last bit of dt -- bit-identical arithmetic is the only way to the
+    same step counts, and the kernel source has it: counts, states and final times equal the oracle's."""
+    n = 120
+    u0, p = C.random_problem(system, n, np.float32, seed=321)
+    dt0 = float(np.float32(0.1))
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=tol, reltol=tol, want_t=True,
+                     dtype=np.float32, n_threads=4)
+    g = _run(emul, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, compat=2)
+    assert np.array_equal(g["retcode"], o.retcode)
+    assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    assert C.bits_equal(_nan_canon(np.ascontiguousarray(g["u"].T)), _nan_canon(np.ascontiguousarray(o.u[:, 0, :])))
+    assert C.bits_equal(_nan_canon(g["t"]), _nan_canon(np.ascontiguousarray(o.t[:, 0])))

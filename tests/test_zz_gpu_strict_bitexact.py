@@ -44,6 +44,13 @@ def host_libm_is_the_restated_one(tmp_path_factory):
             fn(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(y), o.ctypes.data_as(ctypes.c_void_p),
                ctypes.c_long(len(x)))
         ok = ok and bool(np.array_equal(a.view(np.uint64), b.view(np.uint64)))
+    xf = np.ascontiguousarray(x.astype(np.float32))
+    for y in (np.float32(7.0 / 50.0), np.float32(2.0 / 25.0)):
+        a, b = np.empty_like(xf), np.empty_like(xf)
+        for fn, o in ((L.emul_powf_glibc, a), (L.host_libm_powf, b)):
+            fn(xf.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(float(y)), o.ctypes.data_as(ctypes.c_void_p),
+               ctypes.c_long(len(xf)))
+        ok = ok and bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
     return ok
 
 
@@ -64,3 +71,27 @@ def test_strict_controller_fp64_is_the_oracle_bit_for_bit(sde, oracle, host_libm
     assert same_acc == 1.0 and same_rej == 1.0, (same_acc, same_rej)
     assert C.bits_equal(g["u"].T, o.u[:, 0, :]), "max ulp diff %d" % C.max_ulp_diff(g["u"].T, o.u[:, 0, :])
     assert C.bits_equal(g["t_final"], np.full(n, tspan[1]))
+
+
+@pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-4),
+                                                      ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-3),
+                                                      ("lorenz", "GPUSimpleAVern7", (0.0, 5.0), 1e-5),
+                                                      ("lorenz", "GPUSimpleAVern9", (0.0, 5.0), 1e-5)])
+def test_strict_controller_fp32_is_the_oracle_bit_for_bit(sde, oracle, host_libm_is_the_restated_one,
+                                                          system, algname, tspan, tol):
+    """Float32 states: powf is sde_powf_glibc.  The default controller meets only a stated bound in Float32
+    (test_adaptive_fp32_stated_bound: the trailing micro-steps depend on the last bit of dt); the literal
+    one with the oracle's powf must give the oracle's counts and states exactly."""
+    if not host_libm_is_the_restated_one:
+        pytest.skip("this host's libm pow is not the glibc >= 2.28 FMA variant that sde_pow_glibc restates")
+    n = 1000 + 13
+    u0, p = C.random_problem(system, n, np.float32, seed=321)
+    dt0 = float(np.float32(0.1))
+    g = _gpu(sde, system, algname, u0, p, tspan, dt=dt0, abstol=tol, reltol=tol, save_mode=0,
+             compat=sde._lib.COMPAT_STRICT_CONTROLLER)
+    o = _oracle(sde, oracle, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, save_mode=0)
+    assert np.array_equal(g["retcode"], o.retcode)
+    assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    gu, ou = np.ascontiguousarray(g["u"].T), np.ascontiguousarray(o.u[:, 0, :])
+    assert np.array_equal(np.isnan(gu), np.isnan(ou))
+    assert C.bits_equal(np.nan_to_num(gu), np.nan_to_num(ou)), "max ulp diff %d" % C.max_ulp_diff(gu, ou)

@@ -59,13 +59,34 @@ def extract(path):
     if k < 0 or (k - j) % 8:
         raise SystemExit("cannot locate exp_data.tab")
     etab = struct.unpack_from("<%dQ" % (2 * N_EXP), blob, k)
-    # sanity: entry i holds the bits of 2^(i/128) with the exponent field reduced by i (<< 45) and its tail
     import math
+    # sanity: entry i holds the bits of 2^(i/128) with the exponent field reduced by i (<< 45) and its tail
     for q in (1, 37, 127):
         sb = (etab[2 * q + 1] + (q << 45)) & 0xFFFFFFFFFFFFFFFF
         v = struct.unpack("<d", struct.pack("<Q", sb))[0]
         assert abs(v - 2.0 ** (q / 128.0)) < 4e-16, (q, v)
-    return head, tab, ehead, etab
+    # float: struct powf_log2_data { struct { double invc, logc; } tab[16]; double poly[5]; } and
+    # struct exp2f_data { uint64_t tab[32]; double shift_scaled; double poly[3]; ... }
+    # (__log2f_data holds the same table followed by a degree-4 polynomial: take the occurrence whose fifth
+    # coefficient is powf's 1/ln2)
+    fsig = struct.pack("<dd", float.fromhex("0x1.661ec79f8f3bep+0"), float.fromhex("-0x1.efec65b963019p-2"))
+    hits, fi = [], blob.find(fsig)
+    while fi >= 0:
+        if abs(struct.unpack_from("<d", blob, fi + 256 + 32)[0] - 1.0 / math.log(2.0)) < 1e-9:
+            hits.append(fi)
+        fi = blob.find(fsig, fi + 1)
+    if len(hits) != 1:
+        raise SystemExit("cannot locate powf_log2_data uniquely in libm (%d candidates)" % len(hits))
+    fi = hits[0]
+    ftab = struct.unpack_from("<32d", blob, fi)
+    fpoly = struct.unpack_from("<5d", blob, fi + 256)
+    assert any(ftab[2 * q] == 1.0 and ftab[2 * q + 1] == 0.0 for q in range(16))
+    assert abs(fpoly[4] - 1.0 / math.log(2.0)) < 1e-9
+    fj = find_once(blob, struct.pack("<QQ", 0x3FF0000000000000, 0x3FEFD9B0D3158574), "exp2f_data")
+    f2tab = struct.unpack_from("<32Q", blob, fj)
+    f2head = struct.unpack_from("<4d", blob, fj + 256)
+    assert f2head[0] == float.fromhex("0x1.8p+47") and abs(f2head[3] - math.log(2.0)) < 1e-9
+    return head, tab, ehead, etab, ftab, fpoly, f2tab, f2head
 
 
 def main():
@@ -75,7 +96,7 @@ def main():
             if os.path.exists(cand):
                 path = cand
                 break
-    head, tab, ehead, etab = extract(path)
+    head, tab, ehead, etab, ftab, fpoly, f2tab, f2head = extract(path)
     o = []
     o.append("// GENERATED by tools/gen_glibc_pow_tables.py -- do not edit.  Tables and coefficients of glibc's")
     o.append("// table-driven pow (the oracle's libm), used by sde_pow_glibc (sde_common.cuh) on the strict")
@@ -97,6 +118,21 @@ def main():
     o.append("static __device__ const unsigned long long k_gpow_exp[%d] = {" % (2 * N_EXP))
     for k in range(N_EXP):
         o.append("    0x%016xULL, 0x%016xULL," % (etab[2 * k], etab[2 * k + 1]))
+    o.append("};")
+    o.append("// ---- powf: log2 with a 16-entry table, 2^x with a 32-entry table, all in double")
+    for n, v in zip(["kGfA0", "kGfA1", "kGfA2", "kGfA3", "kGfA4"], fpoly):
+        o.append("constexpr double %s = %s;   // %s" % (n, repr(v), v.hex()))
+    for n, v in zip(["kGfShift", "kGfC0", "kGfC1", "kGfC2"], f2head):
+        o.append("constexpr double %s = %s;   // %s" % (n, repr(v), v.hex()))
+    o.append("// {1/c, log2(c)} for the 16 sub-intervals of [0x1.66p-1, 0x1.66p0)")
+    o.append("static __device__ const double k_gpowf_log2[32] = {")
+    for k in range(16):
+        o.append("    %s, %s," % (repr(ftab[2 * k]), repr(ftab[2 * k + 1])))
+    o.append("};")
+    o.append("// bits of 2^(i/32) - (i << 47)")
+    o.append("static __device__ const unsigned long long k_gpowf_exp2[32] = {")
+    for k in range(0, 32, 4):
+        o.append("    " + " ".join("0x%016xULL," % v for v in f2tab[k:k + 4]))
     o.append("};")
     o.append("}  // namespace sde")
     open(OUT, "w").write("\n".join(o) + "\n")
