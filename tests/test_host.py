@@ -175,6 +175,12 @@ def test_nvrtc_user_rhs_compiles_for_sm100a(sde):
         o = sde.api.make_options(alg, np.dtype(np.float64), 4, (0.0, 1.0), 0.1, 1e-6, 1e-3,
                                  np.array([0.5]) if mode == 1 else None, mode, 0, 0, 0, keep)
         assert L.sde_system_prepare(user._handle, ctypes.byref(o)) == 0, L.sde_last_error()
+    # the literal controller (its pow / powf are sde_pow_glibc / sde_powf_glibc with their __device__ tables)
+    for dt_ in (np.float64, np.float32):
+        keep = []
+        o = sde.api.make_options(sde.GPUSimpleAVern7(), np.dtype(dt_), 4, (0.0, 1.0), 0.1, 1e-6, 1e-3, None, 0, 0,
+                                 _lib.COMPAT_STRICT_CONTROLLER, 0, keep)
+        assert L.sde_system_prepare(user._handle, ctypes.byref(o)) == 0, L.sde_last_error()
 
 
 def test_nvrtc_cubin_disk_cache(sde, tmp_path, monkeypatch, capfd):
