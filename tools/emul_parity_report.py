@@ -52,7 +52,8 @@ def main():
             err = np.nanmax(np.abs(g["u"].T - ou) / (tol + tol * np.abs(ou)))
             print("%-34s %-9s %7d %-8s %9.3f%% %14.3g %10d   (%.1f s)" % (
                 name, alg, n, cname, 100 * same, err, int(o.naccept.sum() + o.nreject.sum()), time.time() - t0))
-    print("literal = SDE_COMPAT_STRICT_CONTROLLER: on the host its pow is the oracle's glibc pow, hence 100 % / 0.")
+    print("literal = SDE_COMPAT_STRICT_CONTROLLER: its pow is sde_pow_glibc, the device header's restatement of the oracle's")
+    print("glibc pow (the same IEEE operations run on the GPU), hence 100 % / 0.")
     print("log2 = the default device controller (same formulas in the log2 domain): accept / reject decisions can differ only")
     print("within ~1e-15 of EEst = 1; AVern9 at 1e-12 is the documented exception (its error estimate is rounding noise).")
 
