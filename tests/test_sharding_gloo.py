@@ -72,3 +72,83 @@ def test_two_rank_gloo_sharded_solve_matches_single_process(sde, oracle, tmp_pat
     assert np.array_equal(stats[1], full.min(axis=1)) and np.array_equal(stats[2], full.max(axis=1))
     tmax, count = np.load(tmp_path / "tmax.npy")
     assert tmax == 11.0 and count == n_total
+
+
+def test_cost_weighted_bounds_equalise_a_sorted_sweep(sde):
+    """contiguous ranges of equal estimated cost for adaptive sweeps.  Cost model of the sorted Van der Pol
+    sweep (config 3): accepted steps rise ~8x along the index."""
+    from simplediffeq_b200.sharding import cost_weighted_bounds, pilot_indices, shard_bounds
+    n = 1 << 20
+    true_cost = lambda i: 89.0 + (708.0 - 89.0) * (i / (n - 1.0)) ** 1.5      # noqa: E731
+    idx = pilot_indices(n, 4096)
+    assert idx[0] == 0 and idx[-1] == n - 1 and len(idx) == 4096 and np.all(np.diff(idx) > 0)
+    allc = true_cost(np.arange(n, dtype=np.float64))
+    for world in (1, 2, 4, 8):
+        b = cost_weighted_bounds(n, world, idx, np.round(true_cost(idx)))
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and all(b[i] <= b[i + 1] for i in range(world))
+        per = np.array([allc[b[g]:b[g + 1]].sum() for g in range(world)])
+        assert per.max() / per.mean() < 1.005, per / per.mean()          # balanced to 0.5 %
+        static = np.array([allc[slice(*shard_bounds(n, world, g))].sum() for g in range(world)])
+        if world == 8:
+            assert static.max() / static.mean() > 1.7                      # what equal index ranges would cost
+    # uniform cost -> (almost) the equal-count split; zero / NaN costs and tiny ensembles fall back gracefully
+    b = cost_weighted_bounds(1000, 4, pilot_indices(1000, 64), np.full(64, 7.0))
+    assert b == [0, 250, 500, 750, 1000]
+    assert cost_weighted_bounds(1000, 4, pilot_indices(1000, 64), np.zeros(64)) == [0, 250, 500, 750, 1000]
+    assert cost_weighted_bounds(0, 2, [], []) == [0, 0, 0]
+    assert cost_weighted_bounds(1, 2, [0], [5.0]) in ([0, 0, 1], [0, 1, 1])
+    b = cost_weighted_bounds(10, 2, [0, 9], [np.nan, 4.0])
+    assert b[0] == 0 and b[-1] == 10 and b[1] >= 5
+    with pytest.raises(ValueError):
+        cost_weighted_bounds(10, 2, [3, 3], [1.0, 1.0])
+
+
+def _worker_adaptive(rank, world, port, n_total, out_dir):
+    """Cost-weighted shards of an adaptive Van der Pol sweep: every rank runs the same pilot (the oracle stands in for the
+    device), derives the same bounds without any exchange, solves its range; rank 0 gathers the attempt totals."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    import common as C
+    from simplediffeq_b200.sharding import pilot_weighted_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    u0, p = C.vdp_sweep(n_total)
+    dt0 = float(np.float32(0.1))
+
+    def solve(idx):
+        return oracle_lib.solve("vanderpol", "ATsit5", u0[idx], p[idx], 0.0, 20.0, dt0, abstol=1e-6, reltol=1e-6)
+
+    def pilot(idx):
+        r = solve(idx)
+        return r.naccept + r.nreject
+
+    b = pilot_weighted_bounds(n_total, world, pilot, k=48)
+    r = solve(np.arange(b[rank], b[rank + 1]))
+    mine = torch.tensor([float((r.naccept + r.nreject).sum()), float(b[rank]), float(b[rank + 1])], dtype=torch.float64)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    np.save(os.path.join(out_dir, "a_%d.npy" % rank), np.ascontiguousarray(r.u[:, 0, :]))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "parts.npy"), torch.stack(parts).numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_cost_weighted_adaptive_shards(sde, oracle, tmp_path):
+    import torch.multiprocessing as mp
+    import common as C
+    n_total, world = 1500, 2
+    mp.start_processes(_worker_adaptive, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    parts = np.load(tmp_path / "parts.npy")                       # [rank] = (attempts, lo, hi)
+    assert parts[0][1] == 0 and parts[0][2] == parts[1][1] and parts[1][2] == n_total     # same bounds on both ranks
+    assert parts[0][2] > 0.55 * n_total                           # the cheap end gets more trajectories ...
+    assert abs(parts[0][0] - parts[1][0]) <= 0.03 * parts[:, 0].sum()      # ... and the same work
+    u0, p = C.vdp_sweep(n_total)
+    full = oracle.solve("vanderpol", "ATsit5", u0, p, 0.0, 20.0, float(np.float32(0.1)), abstol=1e-6, reltol=1e-6)
+    got = np.concatenate([np.load(tmp_path / ("a_%d.npy" % r)) for r in range(world)], axis=0)
+    assert got.tobytes() == np.ascontiguousarray(full.u[:, 0, :]).tobytes()
+    half = (full.naccept + full.nreject)[:n_total // 2].sum() / (full.naccept + full.nreject).sum()
+    assert half < 0.42                                            # equal index ranges would be this unbalanced
