@@ -38,6 +38,11 @@ void emul_pow_glibc(const double* x, double y, double* out, long n) { for (long 
 void host_libm_pow(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y); }
 void emul_powf_glibc(const float* x, float y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_powf_glibc(x[i], y); }
 void host_libm_powf(const float* x, float y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y); }
+// element-wise (x[i], y[i]) pairs
+void emul_pow_glibc_xy(const double* x, const double* y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_pow_glibc(x[i], y[i]); }
+void host_libm_pow_xy(const double* x, const double* y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y[i]); }
+void emul_powf_glibc_xy(const float* x, const float* y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = sde::sde_powf_glibc(x[i], y[i]); }
+void host_libm_powf_xy(const float* x, const float* y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = std::pow(x[i], y[i]); }
 int emul_ctrl_count() { return sde::kC_count; }
 double emul_ctrl(int i) { return sde::k_ctrl[i]; }
 }

@@ -191,3 +191,30 @@ def test_strict_controller_powf_is_the_host_libm_powf_bit_for_bit(emul, y):
     assert np.array_equal(np.isnan(a), nan)
     bad = np.flatnonzero(a[~nan].view(np.uint32) != b[~nan].view(np.uint32))
     assert bad.size == 0, (bad.size, x[~nan][bad[:5]], a[~nan][bad[:5]], b[~nan][bad[:5]])
+
+
+@needs_glibc_pow
+def test_glibc_pow_restatement_for_arbitrary_exponents(emul):
+    """Beyond the controller's two exponents: random (x, y) pairs over the whole main-path domain (results from
+    subnormal to near overflow, |y| from 2^-60 to 2^40, negative y), FP64 and FP32 -- the restatement is the libm
+    function, not a fit to two exponents.  (Arguments that leave the main path fall back to the platform pow in both
+    builds and are trivially equal here; the share that stays on the main path is asserted.)"""
+    rng = np.random.default_rng(99)
+    n = 2_000_000
+    x = np.ascontiguousarray(np.exp(rng.uniform(-700, 700, n)))
+    y = np.ascontiguousarray(rng.choice([-1.0, 1.0], n) * np.exp(rng.uniform(np.log(2.0 ** -60), np.log(2.0 ** 40), n)))
+    a, b = np.empty(n), np.empty(n)
+    for fn, out in ((emul.emul_pow_glibc_xy, a), (emul.host_libm_pow_xy, b)):
+        fn(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+           ctypes.c_long(n))
+    main_path = np.abs(y * np.log(x)) < 500
+    assert main_path.mean() > 0.5
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    xf = np.ascontiguousarray(np.exp(rng.uniform(-85, 85, n)).astype(np.float32))
+    yf = np.ascontiguousarray((rng.choice([-1.0, 1.0], n) * np.exp(rng.uniform(-20, 8, n))).astype(np.float32))
+    af, bf = np.empty(n, np.float32), np.empty(n, np.float32)
+    for fn, out in ((emul.emul_powf_glibc_xy, af), (emul.host_libm_powf_xy, bf)):
+        fn(xf.ctypes.data_as(ctypes.c_void_p), yf.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+           ctypes.c_long(n))
+    assert (np.abs(yf.astype(np.float64) * np.log2(xf.astype(np.float64))) < 120).mean() > 0.5
+    assert np.array_equal(af.view(np.uint32), bf.view(np.uint32))
