@@ -189,6 +189,36 @@ def test_adaptive_saveat_and_everystep_device_source(emul, oracle):
     assert C.bits_equal(small["u"], ge["u"][:, :5, :])
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algname", ADAPT)
+def test_literal_controller_series_outputs_are_bit_identical(emul, oracle, algname, dtype):
+    """With the literal controller (own pow = the oracle's libm pow) not only the end points but every series output
+    equals the oracle bit for bit: dense output at `saveat` (both layouts, incl. the never-reached slot) and the
+    variable-length every-step rows with their times -- for ATsit5, AVern7 (extra stages at the advanced time, quirk Q3)
+    and AVern9, in FP64 and FP32."""
+    n = 40
+    u0, p = C.random_problem("lorenz", n, dtype, seed=77)
+    dt0, tol = float(np.float32(0.1)), (1e-8 if dtype is np.float64 else 1e-4)
+    sa = np.array([0.0, 0.3, 0.31, 0.32, 1.0, 1.999, 2.0, 2.5], dtype=dtype)
+    o = oracle.solve("lorenz", C.ALG_NAMES[algname], u0, p, 0.0, 2.0, dt0, abstol=tol, reltol=tol, saveat=sa, dtype=dtype,
+                     n_threads=4)
+    for layout in (0, 1):
+        g = _run(emul, "lorenz", algname, u0, p, (0.0, 2.0), dt0, abstol=tol, reltol=tol, save=1, layout=layout,
+                 saveat=sa, n_out=len(sa), compat=2)
+        u = g["u"] if layout == 0 else np.ascontiguousarray(g["u"].transpose(2, 0, 1))
+        assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+        assert C.bits_equal(_nan_canon(np.ascontiguousarray(u)), _nan_canon(np.ascontiguousarray(o.u)))
+    cap = 400
+    oe = oracle.solve("lorenz", C.ALG_NAMES[algname], u0, p, 0.0, 2.0, dt0, abstol=tol, reltol=tol, dtype=dtype,
+                      save_mode=oracle.SAVE_EVERYSTEP, max_out=cap, want_t=True, n_threads=4)
+    ge = _run(emul, "lorenz", algname, u0, p, (0.0, 2.0), dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=cap, compat=2)
+    assert np.array_equal(ge["naccept"], oe.naccept) and np.array_equal(ge["retcode"], oe.retcode)
+    for i in range(n):
+        k = min(int(oe.n[i]), cap)
+        assert C.bits_equal(np.ascontiguousarray(ge["t"][i, :k]), np.ascontiguousarray(oe.t[i, :k]).astype(dtype))
+        assert C.bits_equal(_nan_canon(np.ascontiguousarray(ge["u"][i, :k])), _nan_canon(np.ascontiguousarray(oe.u[i, :k])))
+
+
 def test_adaptive_failure_exits_device_source(emul, oracle):
     # dt < dtmin: the reference throws error("dt<dtmin"); retcode 1 here (oracle: the same trajectory, same counts)
     u0 = np.ones((3, 1)); p = np.array([[-1e17], [1.01], [-1e17]])

@@ -95,3 +95,38 @@ def test_strict_controller_fp32_is_the_oracle_bit_for_bit(sde, oracle, host_libm
     gu, ou = np.ascontiguousarray(g["u"].T), np.ascontiguousarray(o.u[:, 0, :])
     assert np.array_equal(np.isnan(gu), np.isnan(ou))
     assert C.bits_equal(np.nan_to_num(gu), np.nan_to_num(ou)), "max ulp diff %d" % C.max_ulp_diff(gu, ou)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algname", ["GPUSimpleATsit5", "GPUSimpleAVern7", "GPUSimpleAVern9"])
+def test_strict_controller_series_outputs_are_the_oracle_bit_for_bit(sde, oracle, host_libm_is_the_restated_one,
+                                                                     algname, dtype):
+    """The series outputs under the literal controller: dense output at `saveat` (both layouts) and the
+    variable-length every-step rows with their times, bit for bit (the CPU twin of this test is
+    tests/test_kernel_host_emul.py::test_literal_controller_series_outputs_are_bit_identical)."""
+    if not host_libm_is_the_restated_one:
+        pytest.skip("this host's libm pow is not the glibc >= 2.28 FMA variant that sde_pow_glibc restates")
+    n = 300 + 7
+    u0, p = C.random_problem("lorenz", n, dtype, seed=77)
+    tspan, dt0 = (0.0, 2.0), float(np.float32(0.1))
+    tol = 1e-8 if dtype is np.float64 else 1e-4
+    strict = sde._lib.COMPAT_STRICT_CONTROLLER
+    saveat = np.array([0.0, 0.3, 0.31, 0.32, 1.0, 1.999, 2.0, 2.5], dtype=dtype)
+    o = _oracle(sde, oracle, "lorenz", algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, saveat=saveat)
+    canon = lambda a: np.where(np.isnan(a), np.array(np.nan, dtype=a.dtype), a)      # noqa: E731
+    for layout in (0, 1):
+        g = _gpu(sde, "lorenz", algname, u0, p, tspan, dt=dt0, abstol=tol, reltol=tol, saveat=saveat, save_mode=1,
+                 layout=layout, compat=strict)
+        gu = g["u"] if layout == 0 else np.transpose(g["u"], (2, 0, 1))
+        assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+        assert C.bits_equal(canon(np.ascontiguousarray(gu)), canon(np.ascontiguousarray(o.u)))
+    oe = oracle.solve("lorenz", C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=tol, reltol=tol, dtype=dtype,
+                      save_mode=oracle.SAVE_EVERYSTEP, max_out=2000, want_t=True, n_threads=8)
+    cap = int(oe.naccept.max()) + 1
+    ge = _gpu(sde, "lorenz", algname, u0, p, tspan, dt=dt0, abstol=tol, reltol=tol, save_mode=2, layout=0,
+              out_capacity=cap, compat=strict)
+    assert np.array_equal(ge["naccept"], oe.naccept) and np.all(ge["retcode"] == 0)
+    for i in range(n):
+        k = int(oe.naccept[i]) + 1
+        assert C.bits_equal(np.ascontiguousarray(ge["t_series"][i, :k]), np.ascontiguousarray(oe.t[i, :k]).astype(dtype))
+        assert C.bits_equal(canon(np.ascontiguousarray(ge["u"][i, :k])), canon(np.ascontiguousarray(oe.u[i, :k])))
