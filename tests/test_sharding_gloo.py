@@ -152,3 +152,29 @@ def test_two_rank_gloo_cost_weighted_adaptive_shards(sde, oracle, tmp_path):
     assert got.tobytes() == np.ascontiguousarray(full.u[:, 0, :]).tobytes()
     half = (full.naccept + full.nreject)[:n_total // 2].sum() / (full.naccept + full.nreject).sum()
     assert half < 0.42                                            # equal index ranges would be this unbalanced
+
+
+def test_cost_weighted_bounds_properties_random_profiles(sde):
+    """Random positive cost profiles (smooth, stepped, with zero stretches): bounds are monotone, cover [0, n) once,
+    and no rank's true cost exceeds the mean by more than the profile's resolution allows."""
+    from simplediffeq_b200.sharding import cost_weighted_bounds, pilot_indices
+    rng = np.random.default_rng(8)
+    for trial in range(40):
+        n = int(rng.integers(1, 200_000))
+        world = int(rng.choice([1, 2, 3, 4, 8]))
+        k = int(rng.choice([2, 16, 256, 4096]))
+        i = np.arange(n, dtype=np.float64) / max(n - 1, 1)
+        kind = trial % 3
+        if kind == 0:
+            cost = 50 + 400 * i ** rng.uniform(0.3, 3.0)
+        elif kind == 1:
+            cost = 100 + 80 * np.sin(2 * np.pi * rng.uniform(0.5, 2.0) * i) + 300 * (i > rng.uniform(0.2, 0.8))
+        else:
+            cost = np.where(i < rng.uniform(0.1, 0.5), 0.0, 200.0 * i)
+        idx = pilot_indices(n, k)
+        b = cost_weighted_bounds(n, world, idx, np.round(cost[idx]))
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == n
+        assert all(0 <= b[g] <= b[g + 1] <= n for g in range(world))
+        if kind == 0 and n >= 50_000 and k >= 256:
+            per = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
+            assert per.max() <= 1.02 * per.mean(), (n, world, k, per / per.mean())
