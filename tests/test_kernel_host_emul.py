@@ -458,6 +458,23 @@ def test_work_queue_with_32_lanes_equals_one_lane(warp32, emul, oracle, system, 
     assert np.all(g32["retcode"] == 0)
 
 
+@pytest.mark.parametrize("system,algname,tspan,tol", [("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6),
+                                                      ("lorenz", "GPUSimpleAVern9", (0.0, 10.0), 1e-12)])
+def test_literal_controller_with_32_lanes_is_the_oracle_bit_for_bit(warp32, oracle, system, algname, tspan, tol):
+    """Literal controller under full warps: 32 lanes with unequal step counts drain the work queue (late accept branch,
+    vote exit, lanes in different controller branches) -- every trajectory still equals the oracle bit for bit, config 4
+    included."""
+    n = 150
+    u0, p = (C.lorenz_sweep(n) if system == "lorenz" else C.vdp_sweep(n, shuffled=True))
+    dt0 = float(np.float32(0.1))
+    g = _run(warp32, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, compat=2)
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=tol, reltol=tol, want_t=True,
+                     n_threads=4)
+    assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    assert C.bits_equal(np.ascontiguousarray(g["u"].T), np.ascontiguousarray(o.u[:, 0, :]))
+    assert C.bits_equal(g["t"], np.ascontiguousarray(o.t[:, 0]))
+
+
 @pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8),
                                                       ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6),
                                                       ("lorenz", "GPUSimpleAVern7", (0.0, 10.0), 1e-10),
