@@ -317,6 +317,45 @@ def test_fixed_saveat_device_source_vs_reference_source_execution(emul, sde, cas
     assert C.bits_equal(canon(g["u"][0]), canon(exp_u)), "max ulp diff %d" % C.max_ulp_diff(g["u"][0], exp_u)
 
 
+_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH)
+           if c["alg"] in J.ADAPTIVE and "error" not in c and c["system"] in SYS_ID]
+
+
+@pytest.mark.parametrize("case", _JADAPT, ids=[c["name"] for c in _JADAPT])
+def test_adaptive_literal_controller_vs_reference_source_execution(emul, case):
+    """Every adaptive case of the two reference-source fixtures -- the reference's own `solve` text executed by
+    oracle/jlmini, whose `@fastmath ^` is the C library's pow / powf -- against the device kernels with the literal
+    controller (own pow = that library's operation sequence): accepted-step times, every stored state, dense output at
+    `saveat`, FP64 and FP32, BIT FOR BIT, with no oracle in between."""
+    a = J.case_inputs(case)
+    dtype = a["dtype"]
+    exp_t, exp_u = J.expected(case)
+    u0, p = a["u0"][None, :], a["p"][None, :]
+    tspan = (float(a["t0"]), float(a["tf"]))
+    kw = dict(abstol=float(a["abstol"]), reltol=float(a["reltol"]), compat=2)
+    canon = lambda x: np.where(np.isnan(x), np.array(np.nan, dtype=x.dtype), x)      # noqa: E731
+    if a["kind"] == "endpoint":
+        g = _run(emul, case["system"], case["alg"], u0, p, tspan, float(a["dt"]), **kw)
+        got_u, got_t = np.ascontiguousarray(g["u"].T), g["t"]
+        want_u, want_t = np.ascontiguousarray(exp_u[-1:]), exp_t[-1:]
+    elif a["kind"] == "saveat":
+        g = _run(emul, case["system"], case["alg"], u0, p, tspan, float(a["dt"]), save=1, layout=0, saveat=a["saveat"],
+                 n_out=len(a["saveat"]), **kw)
+        got_u, want_u, got_t, want_t = g["u"][0], exp_u, None, None
+    else:
+        cap = case["n_out"] + 2
+        g = _run(emul, case["system"], case["alg"], u0, p, tspan, float(a["dt"]), save=2, layout=0, n_out=cap, **kw)
+        assert g["naccept"][0] + 1 == case["n_out"], "accepted steps + 1"
+        got_u, want_u = g["u"][0, :case["n_out"]], exp_u
+        got_t, want_t = g["t"][0, :case["n_out"]], exp_t
+        assert np.all(np.isnan(g["u"][0, case["n_out"]:]))
+    assert g["retcode"][0] == 0
+    assert C.bits_equal(canon(np.ascontiguousarray(got_u)), canon(np.ascontiguousarray(want_u))), \
+        "max ulp diff %d" % C.max_ulp_diff(np.ascontiguousarray(got_u), np.ascontiguousarray(want_u))
+    if got_t is not None and want_t.dtype == got_t.dtype:        # ts has eltype(dt) in the reference (quirk Q11)
+        assert C.bits_equal(np.ascontiguousarray(got_t), np.ascontiguousarray(want_t))
+
+
 # ---- SimpleEM device source (csrc/device/sde_em.cuh) ---------------------------------------------------------------
 import jlmini_em_cases as JE  # noqa: E402
 

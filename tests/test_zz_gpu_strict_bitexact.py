@@ -130,3 +130,38 @@ def test_strict_controller_series_outputs_are_the_oracle_bit_for_bit(sde, oracle
         k = int(oe.naccept[i]) + 1
         assert C.bits_equal(np.ascontiguousarray(ge["t_series"][i, :k]), np.ascontiguousarray(oe.t[i, :k]).astype(dtype))
         assert C.bits_equal(canon(np.ascontiguousarray(ge["u"][i, :k])), canon(np.ascontiguousarray(oe.u[i, :k])))
+
+
+import jlmini_cases as J  # noqa: E402
+
+_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH) if c["alg"] in J.ADAPTIVE and "error" not in c]
+
+
+@pytest.mark.parametrize("case", _JADAPT, ids=[c["name"] for c in _JADAPT])
+def test_strict_controller_vs_reference_source_execution_bit_for_bit(sde, host_libm_is_the_restated_one, case):
+    """The adaptive cases of the reference-source fixtures (the reference's own `solve` text run by oracle/jlmini with
+    the C library's pow / powf) through the public API with the literal controller: every stored state and time bit
+    for bit, no oracle in between.  CPU twin: tests/test_kernel_host_emul.py::
+    test_adaptive_literal_controller_vs_reference_source_execution (78 cases, green)."""
+    if not host_libm_is_the_restated_one:
+        pytest.skip("this host's libm pow is not the glibc >= 2.28 FMA variant that sde_pow_glibc restates")
+    a = J.case_inputs(case)
+    dtype = a["dtype"]
+    system = getattr(sde.systems, case["system"], None)
+    if system is None:
+        pytest.skip("no built-in system %s" % case["system"])
+    prob = sde.ODEProblem(system, a["u0"], (a["t0"], a["tf"]), a["p"])
+    alg = getattr(sde, case["alg"])()
+    kw = {k: (np.asarray(v, dtype=dtype) if k == "saveat" else (dtype(v) if k in ("dt", "abstol", "reltol") else v))
+          for k, v in case["kw"].items()}
+    exp_t, exp_u = J.expected(case)
+    sol = sde.solve(prob, alg, compat=sde._lib.COMPAT_STRICT_CONTROLLER, **kw)
+    assert sol.retcode == "Default"
+    su = np.ascontiguousarray(np.asarray(sol.u))
+    assert su.shape == exp_u.shape, (su.shape, exp_u.shape)
+    canon = lambda x: np.where(np.isnan(x), np.array(np.nan, dtype=x.dtype), x)      # noqa: E731
+    assert su.dtype == exp_u.dtype
+    assert C.bits_equal(canon(su), canon(exp_u)), "max ulp diff %d" % C.max_ulp_diff(su, exp_u)
+    st = np.ascontiguousarray(np.asarray(sol.t))
+    if st.dtype == exp_t.dtype and len(st) == len(exp_t):
+        assert C.bits_equal(st, exp_t)
