@@ -16,6 +16,8 @@ F01 = np.float32(0.1)
 
 
 RANDOM_PATH = os.path.join(HERE, "golden", "golden_jlmini_random_v1.json")
+# the adaptive BASELINE configurations (whole accepted-step sequences): oracle/jlmini/gen_golden_configs.py
+CONFIGS_PATH = os.path.join(HERE, "golden", "golden_jlmini_configs_v1.json")
 
 
 def load_cases(path=PATH):

@@ -317,7 +317,7 @@ def test_fixed_saveat_device_source_vs_reference_source_execution(emul, sde, cas
     assert C.bits_equal(canon(g["u"][0]), canon(exp_u)), "max ulp diff %d" % C.max_ulp_diff(g["u"][0], exp_u)
 
 
-_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH)
+_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH) + J.load_cases(J.CONFIGS_PATH)
            if c["alg"] in J.ADAPTIVE and "error" not in c and c["system"] in SYS_ID]
 
 

@@ -18,7 +18,11 @@ import common as C
 import oracle_lib as O
 from jlmini_cases import load_cases, case_inputs, expected, oracle_run
 
-CASES = load_cases()
+from jlmini_cases import CONFIGS_PATH
+
+# + the adaptive BASELINE configurations with every accepted step on record (24 cases: config 1, config 3, AVern7 at
+#   1e-10 and config 4 = AVern9 at 1e-12, 60 ... 831 states each)
+CASES = load_cases() + load_cases(CONFIGS_PATH)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])

@@ -10,7 +10,7 @@ statement on the device.
 
 STATUS: written when the round's GPU minutes were spent -- the CPU side (both tests above) is green, the
 device side had not been run when this file was committed; the test bodies themselves were exercised with the
-host emulation standing in for the device (tools/dryrun_gpu_strict_tests.py: all 92 pass).  The file sorts
+host emulation standing in for the device (tools/dryrun_gpu_strict_tests.py: all 116 pass).  The file sorts
 last so that `-x` reaches every other GPU test first.
 
 The test is skipped when the host's libm is not the one the device function restates (checked directly: the
@@ -138,7 +138,7 @@ def test_strict_controller_series_outputs_are_the_oracle_bit_for_bit(sde, oracle
 
 import jlmini_cases as J  # noqa: E402
 
-_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH) if c["alg"] in J.ADAPTIVE and "error" not in c]
+_JADAPT = [c for c in J.load_cases() + J.load_cases(J.RANDOM_PATH) + J.load_cases(J.CONFIGS_PATH) if c["alg"] in J.ADAPTIVE and "error" not in c]
 
 
 @pytest.mark.parametrize("case", _JADAPT, ids=[c["name"] for c in _JADAPT])
@@ -146,7 +146,7 @@ def test_strict_controller_vs_reference_source_execution_bit_for_bit(sde, host_l
     """The adaptive cases of the reference-source fixtures (the reference's own `solve` text run by oracle/jlmini with
     the C library's pow / powf) through the public API with the literal controller: every stored state and time bit
     for bit, no oracle in between.  CPU twin: tests/test_kernel_host_emul.py::
-    test_adaptive_literal_controller_vs_reference_source_execution (78 cases, green)."""
+    test_adaptive_literal_controller_vs_reference_source_execution (102 cases, green)."""
     if not host_libm_is_the_restated_one:
         pytest.skip("this host's libm pow is not the glibc >= 2.28 FMA variant that sde_pow_glibc restates")
     a = J.case_inputs(case)
