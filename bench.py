@@ -220,6 +220,27 @@ def config0_atsit5(S, oracle_lib, cores, dev):
             "identical_step_counts_frac": float(np.mean(g["naccept"] == o.naccept))}
 
 
+def literal_controller_parity(S, oracle_lib, cores, dev):
+    """Outside every timed region: the literal controller (SDE_COMPAT_STRICT_CONTROLLER, whose pow is the oracle's libm
+    pow operation for operation) against the oracle on samples of BASELINE configs[0] (ATsit5, 1e-8) and configs[3]
+    (AVern9, 1e-12 -- the configuration whose step sequence hangs on the last bit of that pow): share of trajectories
+    with identical accepted AND rejected counts, share with bit-identical final states."""
+    from simplediffeq_b200 import _lib
+    dt0 = float(np.float32(0.1))
+    out = {}
+    for name, oalg, alg, n, tol in (("config0_atsit5_1e-8", "ATsit5", S.GPUSimpleATsit5(), 4096, 1e-8),
+                                    ("config3_avern9_1e-12", "AVern9", S.GPUSimpleAVern9(), 4096, 1e-12)):
+        u0, p = lorenz_inputs_np(0, n, n)
+        o = oracle_lib.solve("lorenz", oalg, u0.T, p.T, 0.0, 10.0, dt0, abstol=tol, reltol=tol, n_threads=cores)
+        g = S.solve_arrays(S.systems.lorenz, alg, u0, p, (0.0, 10.0), dt=dt0, abstol=tol, reltol=tol,
+                           compat=_lib.COMPAT_STRICT_CONTROLLER, devices=[dev.index or 0])
+        gu, ou = np.ascontiguousarray(g["u"].T), np.ascontiguousarray(o.u[:, 0, :])
+        out[name] = {"trajectories": n,
+                     "identical_step_counts_frac": float(np.mean((g["naccept"] == o.naccept) & (g["nreject"] == o.nreject))),
+                     "bit_identical_final_state_frac": float(np.mean(np.all(gu.view(np.uint64) == ou.view(np.uint64), axis=1)))}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; Julia unavailable) on all
     host threads, one bounded sample per step."""
@@ -416,6 +437,10 @@ def main():
                                     "sample": "%d of 10M trajectories x 10000 steps in %.1f s, %d std::threads (C++ restatement of GPUSimpleTsit5; Julia unavailable)" % (n_s, secs, cores)}
             line["parity_spot_check"] = {"trajectories": 512, "bit_identical_to_oracle": same}
             line["config0_atsit5"] = config0_atsit5(S, oracle_lib, cores, dev)
+            try:        # parity evidence only, after the timed region: reported, never fatal
+                line["literal_controller_parity"] = literal_controller_parity(S, oracle_lib, cores, dev)
+            except Exception as e:
+                line["literal_controller_parity"] = {"error": str(e)[:200]}
             try:        # second roofline of BASELINE.json's metric ("% FP64 FMA / HBM roofline"): the saveat-heavy config
                 line["roofline_hbm_config5"] = config5_hbm_roofline(S, torch, dev, peaks)
             except Exception as e:    # e.g. not enough free memory next to another tenant: reported, never fatal
