@@ -94,19 +94,25 @@ enum {
                              steps; the first out_capacity states are stored, naccept tells how many are needed */
 };
 
-/* compat flags: 0 = reproduce the reference exactly, including its quirks */
+/* compat flags: 0 = reproduce the reference exactly, including its quirks.
+   Step-size controller of the adaptive algorithms (src/tsit5/gpuatsit5.jl:276-292): two implementations.
+     literal : the reference's arithmetic operation for operation -- IEEE divisions, sqrt, `EEst^beta1`,
+               `qold^beta2` -- with the pow / powf of the libm a CPU run on an x86-64 Linux host uses (the
+               table-driven pow of glibc >= 2.28 = ARM optimized-routines, FMA variant; one log half shared
+               by both powers).  Reproduces the CPU oracle bit for bit: states, times, accepted and rejected
+               counts.  ~1.3x (AVern9) to 1.5x (ATsit5) the device time of the log2 one.
+     log2    : the same formulas evaluated in the log2 domain (1 log2 + 1 exp2, no division, no sqrt):
+               ~1e-15 relative difference in the next dt; accept / reject decisions unchanged except within
+               ~1e-15 of EEst = 1.
+   With neither flag the library chooses: the literal controller where the step sequence hangs on the last
+   bit of the powers and the log2 one cannot reproduce step counts -- Float32 states, or reltol <= 1e-11
+   (BASELINE config 4, AVern9 at 1e-12) -- and the log2 controller everywhere else (identical accepted-step
+   counts on the BASELINE sweeps at 1e-6 ... 1e-10).  DESIGN.md sections 2 and 6. */
 enum {
   SDE_COMPAT_FIX_VERN9_INTERP = 1, /* fixed-step GPUSimpleVern9 + saveat: use stages 8..15 in the dense
                                       output (the reference uses k2..k9, src/verner/gpuvern9.jl:216-331) */
-  SDE_COMPAT_STRICT_CONTROLLER = 2 /* adaptive: evaluate the PI controller literally (two pow calls, IEEE
-                                      divisions and sqrt, src/tsit5/gpuatsit5.jl:276-292) instead of the
-                                      default log2-domain evaluation of the same formulas (1 log2 + 1 exp2,
-                                      ~1e-15 relative difference in the next dt; accept/reject unchanged
-                                      except within ~1e-15 of EEst = 1).  Its pow / powf is the operation
-                                      sequence of glibc's (>= 2.28, FMA variant), i.e. of the libm a CPU run
-                                      on an x86-64 Linux host uses, so that step sequences that hang on the
-                                      last bit of `EEst^beta1` (AVern9 at 1e-12; every Float32 solve) can be
-                                      reproduced bit for bit (DESIGN.md sections 2 and 6) */
+  SDE_COMPAT_STRICT_CONTROLLER = 2, /* adaptive: force the literal controller */
+  SDE_COMPAT_LOG2_CONTROLLER = 4    /* adaptive: force the log2-domain controller (exclusive with the above) */
 };
 
 typedef struct sde_system_s* sde_system_t;

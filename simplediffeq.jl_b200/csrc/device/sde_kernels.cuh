@@ -371,15 +371,27 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
 
   Method m;
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
-  T t = a.t0, dt = a.dt, told = a.t0, dtold = a.dt, qold = qoldinit;
-  __shared__ __align__(16) double s_ctrl[kC_count];
+  T t = a.t0, dt = a.dt, told = a.t0, dtold = a.dt;
+  // controller constants and tables, one shared-memory copy per CTA: k_ctrl (log2-domain controller) or the
+  // pow / powf tables of the literal one (k_gpow / k_gpowf; per-lane table indices hit shared memory, not LDG)
+  constexpr int kTabCount = kStrict ? (sizeof(T) == 8 ? (int)kGP_count : (int)kGF_count) : (int)kC_count;
+  __shared__ __align__(16) double s_ctrl[kTabCount];
   __shared__ __align__(16) T s_bt[Method::kNBT];
-  for (int i = threadIdx.x; i < kC_count; i += blockDim.x) s_ctrl[i] = k_ctrl[i];
+  {
+    const double* tab_src = kStrict ? (sizeof(T) == 8 ? k_gpow : k_gpowf) : k_ctrl;
+    for (int i = threadIdx.x; i < kTabCount; i += blockDim.x) s_ctrl[i] = tab_src[i];
+  }
   if (threadIdx.x == 0) Method::load_btilde(s_bt);
   __syncthreads();
   const CtrlTab zlane = s_ctrl;
-  const double lqold0 = ctrl_const(zlane, CtrlLog2<T>::kBase + kL_beta2) * ctrl_const(zlane, CtrlLog2<T>::kBase + kL_qoldinit);
-  double lqold = lqold0;   // beta2 * log2(qold)
+  // default controller: lqold = beta2 * log2(qold);  literal controller: qoldpow = qold^beta2 (qold itself is
+  // used nowhere else, and it only changes on accepted attempts)
+  double lqold0 = 0.0;
+  T qoldpow0 = T(0);
+  if (kStrict) qoldpow0 = strict_exp(beta2, strict_log(qoldinit, zlane), zlane);
+  else lqold0 = ctrl_const(zlane, CtrlLog2<T>::kBase + kL_beta2) * ctrl_const(zlane, CtrlLog2<T>::kBase + kL_qoldinit);
+  double lqold = lqold0;
+  T qoldpow = qoldpow0;
   int cur = 0, nacc = 0, nrej = 0;
   i64 traj = -1;
   bool active = false, drained = false;
@@ -401,8 +413,9 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           traj = (i64)base + __popc(want & ((1u << lane) - 1u));
           if (traj < a.n_traj) {
             load_problem<T, N, NP>(a, traj, u, p);
-            t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt; qold = qoldinit;
+            t = a.t0; dt = a.dt; told = a.t0; dtold = a.dt;
             lqold = lqold0;
+            qoldpow = qoldpow0;
             cur = 0; nacc = 0; nrej = 0;
             m.seed(u, p, t);
   #pragma unroll
@@ -450,9 +463,11 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         T e[N];
         m.error(dt, e, s_bt);
         bool accept;
+        T EEst = T(0);                 // literal controller only: the estimate and the log half of its powers
+        decltype(strict_log(T(1), zlane)) Elog{};
         if (kStrict) {
+          // the reference's arithmetic, operation for operation (gpuatsit5.jl:276-292):
           // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
-          T EEst;
           if (N == 1) {
             EEst = sde_abs(e[0] / (a.abstol + max_abs_nan2(uprev[0], u[0]) * a.reltol));
           } else {
@@ -464,23 +479,27 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
             }
             EEst = sde_sqrt(ssum / T(N));
           }
-          const T q11 = sde_pow(EEst, beta1);
-          T q = (EEst == T(0)) ? inv_qmax : q11 / sde_pow(qold, beta2);
           accept = !(EEst > T(1));
-          if (!accept) {
-            dt = dt / jl_min(inv_qmin, q11 / gamma);
-          } else {
-            q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
-            qold = jl_max(EEst, qoldinit);
-            dtold = dt;
-            dt = dt / q;
-          }
+          // q11 = EEst^beta1: log half once (kept for qold^beta2 below), exp half per exponent; anything but a
+          // positive normal estimate (0, subnormal, inf, NaN) takes the out-of-line complete function
+          Elog = strict_log(EEst, zlane);      // (table indices are masked: harmless for any bit pattern)
+          T q11 = strict_exp(beta1, Elog, zlane);
+          if (!strict_is_main(EEst)) q11 = sde_pow_cold(EEst, beta1);
+          // accept: q = EEst == 0 ? inv(qmax) : q11 / qold^beta2;  q = max(inv(qmax), min(inv(qmin), q / gamma));  dt /= q
+          // reject: dt /= min(inv(qmin), q11 / gamma)     (EEst > 1, so q11 / gamma > 1: the lower clamp is a no-op and
+          //         the NaN rule of Base.min is never exercised)
+          // both as straight-line code: the lanes of a warp part only at the late branch below
+          T q = accept ? q11 / qoldpow : q11;
+          if (EEst == T(0)) q = inv_qmax;
+          q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
+          if (accept) dtold = dt;
+          dt = dt / q;
         } else {
           // same formulas in the log2 domain (see sde_common.cuh); lqold = beta2 * log2(qold)
           constexpr int LB = CtrlLog2<T>::kBase;
           const double one = ctrl_const(zlane, kC_one);
-          double lE;        // log2(EEst); an estimate of exactly zero gives about -1023 (f64: -511), which
-                            // the accept clamp turns into inv(qmax) like the reference's `EEst == 0` branch
+          double lE;        // log2(EEst)
+          bool ezero;       // the reference's `EEst == 0 ? inv(qmax)` branch: q / gamma = 1/9, NOT the clamp's 1/10
           if (sizeof(T) == 8) {
             // EEst^2 = sum((e_i / sc_i)^2) / N with Newton reciprocals: no division, no sqrt
             double ss = 0.0;
@@ -492,10 +511,10 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
             }
             ss = ss * (1.0 / (double)N);
             accept = !(ss > one);
+            ezero = (ss == 0.0);
             lE = (ss != ss) ? ss : ctrl_const(zlane, kC_half) * sde_log2_fast(ss, zlane);
           } else {
             // FP32 state: EEst exactly as the reference (IEEE float div / sqrt), controller in FP64
-            T EEst;
             if (N == 1) {
               EEst = sde_abs(e[0] / (a.abstol + max_abs_nan2(uprev[0], u[0]) * a.reltol));
             } else {
@@ -508,6 +527,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
               EEst = sde_sqrt(ssum / T(N));
             }
             accept = !(EEst > T(1));
+            ezero = (EEst == T(0));
             lE = (EEst != EEst) ? (double)EEst : sde_log2_fast((double)EEst, zlane);
           }
           // reject:  dt /= min(inv(qmin), q11/gamma)                     -> exponent -min(l_invqmin, l11 - l_gamma)
@@ -521,6 +541,7 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           // (on the reject path l11 > 0 > lmax + lg, so the lower clamp is a no-op there and is applied
           //  unconditionally)
           double lx = accept ? l11 - lqold : l11;
+          if (ezero) lx = lmax;            // (log2(0) is about -1023 here; the clamp alone would give 1/qmax instead of 1/qmax/gamma)
           lx = lx - lg;
           lx = max_fast(lmax, min_fast(lmin, lx));
           if (accept) {
@@ -539,6 +560,12 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           if ((double)rem < thr) t = tf;
           else t = t + dtold;
           ++nacc;
+          if (kStrict) {
+            // qold = max(EEst, qoldinit), carried as qold^beta2.  qoldinit < EEst <= 1 is a positive normal number;
+            // Base.max propagates a NaN estimate
+            if (EEst > qoldinit) qoldpow = strict_exp(beta2, Elog, zlane);
+            else qoldpow = (EEst != EEst) ? EEst : qoldpow0;
+          }
           if (SAVE == kSaveEveryStep) {   // push!(us, u); push!(ts, t)   (gpuatsit5.jl:301-303)
             if ((i64)nacc < a.n_out) {
               put_series<T, N>(a, traj, nacc, u);

@@ -36,7 +36,8 @@ static_assert((int)sde::kLayoutTrajMajor == SDE_LAYOUT_TRAJ_MAJOR && (int)sde::k
 static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin == SDE_RET_DTMIN &&
               (int)sde::kRetMaxIters == SDE_RET_MAXITERS && (int)sde::kRetOutputFull == SDE_RET_OUTPUT_FULL, "retcodes");
 static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP &&
-              (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER, "compat flags");
+              (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER &&
+              (int)sde::kCompatLog2Controller == SDE_COMPAT_LOG2_CONTROLLER, "compat flags");
 
 extern const char* const sde_embedded_names[];
 extern const char* const sde_embedded_sources[];
@@ -69,7 +70,14 @@ bool is_adaptive(int alg) { return alg == SDE_ALG_ATSIT5 || alg == SDE_ALG_AVERN
 bool want_q2(const sde_options_t* o) {
   return o->alg == SDE_ALG_VERN9 && o->save_mode == SDE_SAVE_SAVEAT && !(o->compat & SDE_COMPAT_FIX_VERN9_INTERP);
 }
-bool want_strict(const sde_options_t* o) { return is_adaptive(o->alg) && (o->compat & SDE_COMPAT_STRICT_CONTROLLER); }
+// literal or log2-domain step-size controller (see the compat flags in simplediffeq_cuda.h): forced by a flag,
+// otherwise literal exactly where the log2 one cannot reproduce the reference's step counts
+bool want_strict(const sde_options_t* o) {
+  if (!is_adaptive(o->alg)) return false;
+  if (o->compat & SDE_COMPAT_STRICT_CONTROLLER) return true;
+  if (o->compat & SDE_COMPAT_LOG2_CONTROLLER) return false;
+  return o->dtype == SDE_F32 || o->reltol <= 1e-11;
+}
 bool want_staged(const sde_options_t* o) {
   return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
 }
@@ -148,8 +156,10 @@ int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
     return fail(SDE_ERR_INVALID, "unknown layout %d", o->layout);
   if (o->n_traj < 0) return fail(SDE_ERR_INVALID, "n_traj < 0");
-  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER))
+  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER))
     return fail(SDE_ERR_INVALID, "unknown compat flags 0x%x", (unsigned)o->compat);
+  if ((o->compat & SDE_COMPAT_STRICT_CONTROLLER) && (o->compat & SDE_COMPAT_LOG2_CONTROLLER))
+    return fail(SDE_ERR_INVALID, "compat flags SDE_COMPAT_STRICT_CONTROLLER and SDE_COMPAT_LOG2_CONTROLLER exclude each other");
   if (o->save_mode == SDE_SAVE_SAVEAT) {
     if (o->n_save < 0 || (o->n_save > 0 && !o->saveat)) return fail(SDE_ERR_INVALID, "saveat array missing");
     if (o->n_save > 0x7fffffff) return fail(SDE_ERR_INVALID, "n_save too large");
@@ -524,7 +534,8 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   a.t0 = (T)o->t0; a.tf = (T)o->tf; a.dt = (T)o->dt; a.abstol = (T)o->abstol; a.reltol = (T)o->reltol;
   a.n_steps = adaptive ? 0 : o->n_steps;
   a.n_save = o->save_mode == SDE_SAVE_SAVEAT ? (int)o->n_save : 0;
-  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER);   // bit 30 must reach the kernel as 0 (sde::kCompatRuntimeZero)
+  // the kernels only look at kCompatRuntimeZero (bit 30), which must reach them as 0; the variants were chosen by get_kernel
+  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER);
   a.layout = o->layout;
   a.max_attempts = o->max_attempts;
   a.out_u = (T*)d_out_u;
@@ -646,8 +657,17 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSour
     char *u0 = nullptr, *p = nullptr, *out = nullptr, *t = nullptr;
     int32_t *na = nullptr, *nr = nullptr, *rc = nullptr;
   };
+  // the caller's current device is restored on every exit path (a single-device solve runs on the caller's thread)
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
   auto body = [&]() -> int {
-    if (device >= 0) SDE_CUDA(cudaSetDevice(device));
+    if (device >= 0) {
+      int cur = -1;
+      SDE_CUDA(cudaGetDevice(&cur));
+      if (cur != device) { SDE_CUDA(cudaSetDevice(device)); guard.prev = cur; }
+    }
     int dev = 0;
     SDE_CUDA(cudaGetDevice(&dev));
     const size_t es = esize(o->dtype);

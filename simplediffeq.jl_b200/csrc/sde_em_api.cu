@@ -227,8 +227,17 @@ int em_noise_launch(int dtype, uint64_t seed, int64_t traj_offset, int64_t n_tra
 // one device of a host-buffer solve: trajectories [lo, hi) in pieces that fit the memory budget
 int em_solve_shard(sde_em_system_s* sys, const sde_em_options_t* o, int device, int64_t lo, int64_t hi, const char* u0,
                    const char* p, const char* noise, char* out_u, std::string* err) {
+  // the caller's current device is restored on every exit path (a single-device solve runs on the caller's thread)
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
   auto body = [&]() -> int {
-    if (device >= 0) SDE_CUDA(cudaSetDevice(device));
+    if (device >= 0) {
+      int cur = -1;
+      SDE_CUDA(cudaGetDevice(&cur));
+      if (cur != device) { SDE_CUDA(cudaSetDevice(device)); guard.prev = cur; }
+    }
     int dev = 0;
     SDE_CUDA(cudaGetDevice(&dev));
     if (hi <= lo) return SDE_OK;

@@ -11,6 +11,8 @@ sharded), or an explicit `noise` array of standard normals.
 """
 import ctypes
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -244,11 +246,18 @@ def solve_em_device(system, d_u0, d_p, t0, dt, n_steps, *, seed=0, d_noise=None,
     return out
 
 
-def solve_em(prob, alg=None, *, dt=None, trajectories=None, seed=0, noise=None, save_everystep=True,
+def solve_em(prob, alg=None, *, dt=None, trajectories=None, seed=None, noise=None, save_everystep=True,
              layout="traj_major", devices=None, **kwargs):
     """solve(prob, SimpleEM(); dt) / solve(EnsembleProblem(prob; prob_func), SimpleEM(); dt, trajectories).
     Unknown keywords are swallowed like the reference's `kwargs...`.  `seed`, `noise`, `save_everystep=False`
-    (endpoint only), `layout` and `devices` are extensions."""
+    (endpoint only), `layout` and `devices` are extensions.
+    seed=None (default) draws a fresh 64-bit Philox key from the OS for every call, like the reference's `randn` on
+    the task-local RNG: repeated solves give independent paths.  The key that was used is kept on the solution
+    (`sol.seed`) so that a run can be reproduced by passing it back."""
+    if seed is None and noise is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    elif seed is None:
+        seed = 0
     if dt is None:
         raise ValueError("dt required for SimpleEM")        # src/euler_maruyama.jl:51
     single = isinstance(prob, SDEProblem)
@@ -279,4 +288,12 @@ def solve_em(prob, alg=None, *, dt=None, trajectories=None, seed=0, noise=None, 
                           save_mode=save_mode, layout=lay, devices=devices)
     sol = EMEnsembleSolution(n_traj=n, dtype=dtype, save_mode=save_mode, layout=lay, u0_soa=u0_soa, u_raw=raw,
                              t=em_times(base.tspan, dt, dtype), prob=ens, alg=alg)
-    return sol[0] if single else sol
+    sol.seed = seed
+    if single:
+        one = sol[0]
+        try:
+            one.seed = seed
+        except AttributeError:
+            pass
+        return one
+    return sol

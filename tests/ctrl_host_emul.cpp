@@ -7,7 +7,9 @@
 #define SDE_HOST_EMULATION 1
 #define __device__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __constant__
+#define __align__(n) __attribute__((aligned(n)))
 struct double2 { double x, y; };
 static inline int __double2hiint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
 static inline int __double2loint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }

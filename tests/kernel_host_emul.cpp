@@ -31,6 +31,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __constant__
 #define __shared__ static      /* shared by the block's threads; blocks run one after the other */
 // The headers' one non-local shared declaration, `extern __shared__ __align__(16) unsigned char sde_dyn_smem[];`

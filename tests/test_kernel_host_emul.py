@@ -556,3 +556,32 @@ def test_literal_controller_fp32_is_bit_identical(emul, oracle, system, algname,
     assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
     assert C.bits_equal(_nan_canon(np.ascontiguousarray(g["u"].T)), _nan_canon(np.ascontiguousarray(o.u[:, 0, :])))
     assert C.bits_equal(_nan_canon(g["t"]), _nan_canon(np.ascontiguousarray(o.t[:, 0])))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("compat", [0, 2])
+@pytest.mark.parametrize("algname", ADAPT)
+def test_zero_error_estimate_takes_the_references_branch(emul, oracle, algname, compat, dtype):
+    """`q = EEst == 0 ? inv(qmax) : ...` then `q / gamma` (gpuatsit5.jl:283-291): a trajectory sitting at an
+    equilibrium (lineardecay, u0 = 0: every stage is exactly zero) grows dt by qmax * gamma = 9x per step, not by
+    the clamp's 10x.  The log2-domain controller used to take the clamp (advisor finding, round 1): accepted times
+    0.01, 0.11, 1.11, ... instead of 0.01, 0.1, 0.91, 8.2, 73.81, 100.  Every accepted time must equal the oracle's."""
+    n = 5
+    u0 = np.zeros((n, 3), dtype=dtype)
+    u0[1:] = C.random_problem("lineardecay", n - 1, dtype, seed=3)[0]          # neighbours that do move
+    p = np.ones((n, 3), dtype=dtype)
+    tspan, dt0 = (0.0, 100.0), 0.01
+    o = oracle.solve("lineardecay", C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt0, abstol=1e-6, reltol=1e-3,
+                     dtype=dtype, save_mode=oracle.SAVE_EVERYSTEP, max_out=400, want_t=True, n_threads=1)
+    cap = int(o.naccept.max()) + 1
+    g = _run(emul, "lineardecay", algname, u0, p, tspan, dt0, save=2, layout=0, compat=compat, n_out=cap)
+    assert int(o.naccept[0]) == 6
+    assert np.array_equal(g["naccept"][:1], o.naccept[:1]) and np.array_equal(g["nreject"][:1], o.nreject[:1])
+    k = int(o.naccept[0]) + 1
+    gt, ot = np.ascontiguousarray(g["t"][0, :k]), np.ascontiguousarray(o.t[0, :k]).astype(dtype)
+    assert np.all(g["u"][0, :k] == 0)
+    if compat == 2:      # literal controller: bit for bit, everything, everywhere
+        assert C.bits_equal(gt, ot)
+        assert np.array_equal(g["naccept"], o.naccept) and np.array_equal(g["nreject"], o.nreject)
+    else:                # log2-domain controller: the same step sequence, dt within its ~1e-15 (Float32: 1 ulp)
+        assert np.allclose(gt, ot, rtol=1e-13 if dtype is np.float64 else 3e-7, atol=0)
