@@ -14,6 +14,7 @@ the configuration the headline metric is quoted on):
     1b    the same sweep at 2^20 trajectories (a GPU-filling ensemble)
     2     Lorenz 10 M, GPUSimpleTsit5 fixed dt = 1e-3, 10 000 steps, FP64     (configs[1])   [default]
     2f32  the same in Float32
+    2fast the same in FP64 with SDE_COMPAT_FAST_RHS (contracted right-hand side; not bit-identical to the reference)
     3     Van der Pol mu-sweep 2^20, GPUSimpleATsit5 tol 1e-6, sorted         (configs[2])
     3s    the same, shuffled (i -> i * 2654435761 mod n)
     4     Lorenz 1 M, GPUSimpleAVern9 tol 1e-12 (default options = literal controller)   (configs[3])
@@ -64,6 +65,11 @@ CONFIGS = {
     "2f32": dict(baseline="configs[1] in Float32", system="lorenz", alg="GPUSimpleTsit5", oalg="Tsit5", n=10_000_000, tspan=(0.0, 10.0), dt=1e-3,
                  dtype="f32", desc="Lorenz rho-sweep 10M trajectories, GPUSimpleTsit5 fixed dt=0.001, 10000 steps, FP32, endpoint only",
                  instr=127, flop=190),
+    "2fast": dict(baseline="configs[1] with SDE_COMPAT_FAST_RHS", system="lorenz", alg="GPUSimpleTsit5", oalg="Tsit5", n=10_000_000,
+                  tspan=(0.0, 10.0), dt=1e-3, compat=8, instr=115, flop=190,
+                  desc="Lorenz rho-sweep 10M trajectories, GPUSimpleTsit5 fixed dt=0.001, FP64, endpoint only, contracted right-hand side "
+                       "(SDE_COMPAT_FAST_RHS: 114 instead of 126 FP64 operations per step; NOT bit-identical to the reference, <= 1e-12 "
+                       "relative on this sweep; the same 190 flops per step are counted)"),
     "3": dict(baseline="configs[2] sorted", system="vanderpol", alg="GPUSimpleATsit5", oalg="ATsit5", n=1 << 20, tspan=(0.0, 20.0), tol=1e-6,
               desc="Van der Pol mu-sweep 2^20 trajectories (sorted), GPUSimpleATsit5 abstol=reltol=1e-6, tspan (0,20), endpoint only", instr=150),
     "3s": dict(baseline="configs[2] shuffled", system="vanderpol", alg="GPUSimpleATsit5", oalg="ATsit5", n=1 << 20, tspan=(0.0, 20.0), tol=1e-6,
@@ -86,7 +92,7 @@ CONFIGS = {
                saveat=(0.0, 0.01, 10.0), layout="soa", instr=151,
                desc="Lorenz 4M trajectories, GPUSimpleTsit5 dt=0.01 (1000 steps, ~1 save point per step) + saveat=0:0.01:10, SoA"),
 }
-EXTRA_ORDER = ["2f32", "1", "1b", "3", "3s", "4", "4l", "5", "5f", "5tm"]
+EXTRA_ORDER = ["2f32", "2fast", "1", "1b", "3", "3s", "4", "4l", "5", "5f", "5tm"]
 
 
 def is_adaptive(cfg):
@@ -138,6 +144,11 @@ def inputs_np_idx(cfg, idx, n_total):
 
 def inputs_np(cfg, lo, hi, n_total):
     return inputs_np_idx(cfg, np.arange(lo, hi, dtype=np.int64), n_total)
+
+
+def lorenz_inputs_np(lo, hi, n_total, dtype=np.float64):
+    """Config 2's inputs for the index range [lo, hi) of a sweep of n_total (also used by tests/test_sharding_gloo.py)."""
+    return inputs_np(CONFIGS["2f32" if dtype is np.float32 else "2"], lo, hi, n_total)
 
 
 def inputs_torch(cfg, lo, hi, n_total, dev, torch):
@@ -367,7 +378,8 @@ class Bench:
             out = torch.empty_like(d_u0)
 
             def launch():
-                st["out"] = S.solve_device(sysm, alg, d_u0, d_p, cfg["tspan"], dt=cfg["dt"], out=out, stats=False, sync=False)
+                st["out"] = S.solve_device(sysm, alg, d_u0, d_p, cfg["tspan"], dt=cfg["dt"], out=out, stats=False, sync=False,
+                                           compat=cfg.get("compat", 0))
         return launch, st, (d_u0, d_p)
 
     def time_launches(self, launch, warmup, steps, sample_clocks=False):

@@ -20,6 +20,7 @@ RET_DEFAULT, RET_DTMIN, RET_MAXITERS, RET_OUTPUT_FULL = 0, 1, 2, 3
 COMPAT_FIX_VERN9_INTERP = 1
 COMPAT_STRICT_CONTROLLER = 2
 COMPAT_LOG2_CONTROLLER = 4
+COMPAT_FAST_RHS = 8
 
 EXPORTS = ["sde_version", "sde_last_error", "sde_device_count", "sde_system_builtin",
            "sde_system_nvrtc", "sde_system_dims", "sde_system_free", "sde_system_prepare",

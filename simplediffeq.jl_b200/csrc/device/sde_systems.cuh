@@ -24,6 +24,21 @@ struct Lorenz {
   }
 };
 
+// SDE_COMPAT_FAST_RHS twin of Lorenz: the same right-hand side with its multiply-add pairs contracted (8 -> 6 FP64
+// instructions per evaluation; a fixed-step Tsit5 step 126 -> 114).  NOT the reference's arithmetic (its f is never
+// under @muladd): results differ from the reference-exact kernels in the last bits of every stage -- <= 1e-12 relative
+// over BASELINE config 2's non-chaotic rho-sweep except next to the homoclinic bifurcation at rho = 13.926 (6e-12; GPU
+// test), unbounded in a chaotic regime like any rounding change.
+struct LorenzFma {
+  static constexpr int N = 3, NP = 3;
+  template <class T>
+  __device__ __forceinline__ static void rhs(T* du, const T* u, const T* p, T) {
+    du[0] = p[0] * (u[1] - u[0]);
+    du[1] = fma(u[0], p[1] - u[2], -u[1]);
+    du[2] = fma(u[0], u[1], -(p[2] * u[2]));
+  }
+};
+
 // u1' = u2 ; u2' = p1*(1-u1*u1)*u2 - u1      (Julia: p[1]*(1-u[1]*u[1])*u[2]-u[1])
 struct VanDerPol {
   static constexpr int N = 2, NP = 1;
@@ -31,6 +46,16 @@ struct VanDerPol {
   __device__ __forceinline__ static void rhs(T* du, const T* u, const T* p, T) {
     du[0] = u[1];
     du[1] = (p[0] * (T(1) - u[0] * u[0])) * u[1] - u[0];
+  }
+};
+
+// SDE_COMPAT_FAST_RHS twin of VanDerPol (5 -> 3 FP64 instructions per evaluation)
+struct VanDerPolFma {
+  static constexpr int N = 2, NP = 1;
+  template <class T>
+  __device__ __forceinline__ static void rhs(T* du, const T* u, const T* p, T) {
+    du[0] = u[1];
+    du[1] = fma(p[0] * fma(-u[0], u[0], T(1)), u[1], -u[0]);
   }
 };
 

@@ -37,7 +37,8 @@ static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin ==
               (int)sde::kRetMaxIters == SDE_RET_MAXITERS && (int)sde::kRetOutputFull == SDE_RET_OUTPUT_FULL, "retcodes");
 static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP &&
               (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER &&
-              (int)sde::kCompatLog2Controller == SDE_COMPAT_LOG2_CONTROLLER, "compat flags");
+              (int)sde::kCompatLog2Controller == SDE_COMPAT_LOG2_CONTROLLER &&
+              (int)sde::kCompatFastRhs == SDE_COMPAT_FAST_RHS, "compat flags");
 
 extern const char* const sde_embedded_names[];
 extern const char* const sde_embedded_sources[];
@@ -113,6 +114,7 @@ struct sde_system_s {
   std::string name;
   int n_state = 0, n_param = 0;
   sde_builtin_lookup_fn lookup = nullptr;
+  sde_builtin_lookup_fn lookup_fast = nullptr;   // SDE_COMPAT_FAST_RHS twin (contracted right-hand side), if any
   // NVRTC systems
   std::string src;
   std::mutex mu;
@@ -125,15 +127,16 @@ struct BuiltinEntry {
   const char* name;
   int n_state, n_param;
   sde_builtin_lookup_fn fn;
+  sde_builtin_lookup_fn fn_fast;   // SDE_COMPAT_FAST_RHS twin or null
 };
 const BuiltinEntry kBuiltins[] = {
-    {"lorenz", 3, 3, sde_lookup_lorenz},
-    {"vanderpol", 2, 1, sde_lookup_vanderpol},
-    {"robertson", 3, 3, sde_lookup_robertson},
-    {"nbody", 12, 3, sde_lookup_nbody},
-    {"lineardecay", 3, 3, sde_lookup_lineardecay},
-    {"scalargrowth", 1, 1, sde_lookup_scalargrowth},
-    {"nonautonomous", 2, 2, sde_lookup_nonautonomous},
+    {"lorenz", 3, 3, sde_lookup_lorenz, sde_lookup_lorenz_fma},
+    {"vanderpol", 2, 1, sde_lookup_vanderpol, sde_lookup_vanderpol_fma},
+    {"robertson", 3, 3, sde_lookup_robertson, nullptr},
+    {"nbody", 12, 3, sde_lookup_nbody, nullptr},
+    {"lineardecay", 3, 3, sde_lookup_lineardecay, nullptr},
+    {"scalargrowth", 1, 1, sde_lookup_scalargrowth, nullptr},
+    {"nonautonomous", 2, 2, sde_lookup_nonautonomous, nullptr},
 };
 sde_system_s g_builtin_handles[sizeof(kBuiltins) / sizeof(kBuiltins[0])];
 std::once_flag g_builtin_once;
@@ -145,6 +148,7 @@ void init_builtins() {
     g_builtin_handles[i].n_state = kBuiltins[i].n_state;
     g_builtin_handles[i].n_param = kBuiltins[i].n_param;
     g_builtin_handles[i].lookup = kBuiltins[i].fn;
+    g_builtin_handles[i].lookup_fast = kBuiltins[i].fn_fast;
   }
 }
 
@@ -156,7 +160,7 @@ int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
     return fail(SDE_ERR_INVALID, "unknown layout %d", o->layout);
   if (o->n_traj < 0) return fail(SDE_ERR_INVALID, "n_traj < 0");
-  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER))
+  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS))
     return fail(SDE_ERR_INVALID, "unknown compat flags 0x%x", (unsigned)o->compat);
   if ((o->compat & SDE_COMPAT_STRICT_CONTROLLER) && (o->compat & SDE_COMPAT_LOG2_CONTROLLER))
     return fail(SDE_ERR_INVALID, "compat flags SDE_COMPAT_STRICT_CONTROLLER and SDE_COMPAT_LOG2_CONTROLLER exclude each other");
@@ -278,7 +282,7 @@ static void cache_store(const std::string& dir, const std::string& path, const s
   if (!ok || rename(t.c_str(), path.c_str()) != 0) remove(t.c_str());   // atomic publish
 }
 
-int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log) {
+int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log, bool fmad) {
   const bool trace = getenv("SDE_TRACE") != nullptr;
   char tune_k[96], tune32_k[96];
   {
@@ -286,7 +290,9 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
     snprintf(tune_k, sizeof tune_k, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 45);
     snprintf(tune32_k, sizeof tune32_k, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 93);
   }
-  const char* key_opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
+  // --fmad=false: only explicit fma() fuses (the reference's @muladd placement; the user's f rounds as written).
+  // SDE_COMPAT_FAST_RHS compiles the program with --fmad=true instead.
+  const char* key_opts[] = {"--gpu-architecture=sm_100a", fmad ? "--fmad=true" : "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
   std::string dir, path;
   if (cubin) {
     dir = cache_dir();
@@ -338,15 +344,16 @@ namespace {
 // returns the cache entry (compiled; module loaded only if `load`)
 int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
   const bool q2 = want_q2(o), strict = want_strict(o), staged = want_staged(o);
+  const bool fast = (o->compat & SDE_COMPAT_FAST_RHS) != 0;
   int dev = -1;
   if (load) SDE_CUDA(cudaGetDevice(&dev));
   char key[96];
-  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict, (int)staged);
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict, (int)staged, (int)fast);
   std::lock_guard<std::mutex> lk(sys->mu);
   Compiled& c = sys->cache[key];
   if (c.cubin.empty()) {
     std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, staged, false);
-    int rc = nvrtc_compile(prog, &c.cubin, nullptr);
+    int rc = nvrtc_compile(prog, &c.cubin, nullptr, fast);
     if (rc != SDE_OK) { sys->cache.erase(key); return rc; }
   }
   if (!load) return SDE_OK;
@@ -365,7 +372,8 @@ int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const 
 
 int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
   if (sys->builtin) {
-    sde::KernelInfo ki = sys->lookup(o->alg, o->dtype, o->save_mode,
+    const sde_builtin_lookup_fn look = ((o->compat & SDE_COMPAT_FAST_RHS) && sys->lookup_fast) ? sys->lookup_fast : sys->lookup;
+    sde::KernelInfo ki = look(o->alg, o->dtype, o->save_mode,
                                      (want_q2(o) ? 1 : 0) | (want_strict(o) ? 2 : 0) | (want_staged(o) ? 4 : 0));
     if (!ki.fn)
       return fail(SDE_ERR_UNSUPPORTED, "no kernel for system %s alg %d dtype %d save_mode %d",
@@ -535,7 +543,7 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   a.n_steps = adaptive ? 0 : o->n_steps;
   a.n_save = o->save_mode == SDE_SAVE_SAVEAT ? (int)o->n_save : 0;
   // the kernels only look at kCompatRuntimeZero (bit 30), which must reach them as 0; the variants were chosen by get_kernel
-  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER);
+  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS);
   a.layout = o->layout;
   a.max_attempts = o->max_attempts;
   a.out_u = (T*)d_out_u;
@@ -861,7 +869,7 @@ int sde_system_nvrtc(const char* src, int n_state, int n_param, sde_system_t* ou
   // syntax check now (both element types must compile), kernels are built lazily
   for (int dtype = 0; dtype < 2; ++dtype) {
     std::string lg;
-    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, false, false, true), nullptr, &lg);
+    int rc = nvrtc_compile(user_program(s, 0, dtype, 0, false, false, false, true), nullptr, &lg, false);
     if (rc != SDE_OK) {
       if (log && log_len) { strncpy(log, lg.c_str(), log_len - 1); log[log_len - 1] = '\0'; }
       delete s;

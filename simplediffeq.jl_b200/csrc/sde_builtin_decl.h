@@ -20,3 +20,6 @@ sde::KernelInfo sde_lookup_nbody(int, int, int, int);
 sde::KernelInfo sde_lookup_lineardecay(int, int, int, int);
 sde::KernelInfo sde_lookup_scalargrowth(int, int, int, int);
 sde::KernelInfo sde_lookup_nonautonomous(int, int, int, int);
+// SDE_COMPAT_FAST_RHS twins (contracted right-hand sides)
+sde::KernelInfo sde_lookup_lorenz_fma(int, int, int, int);
+sde::KernelInfo sde_lookup_vanderpol_fma(int, int, int, int);

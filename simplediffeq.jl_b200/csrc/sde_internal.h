@@ -28,7 +28,7 @@ int device_pool(int dev, cudaMemPool_t* out);
 size_t pool_keep_bytes();
 
 // NVRTC: compile `program` (device headers are embedded in the library) to a cubin for sm_100a
-int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log);
+int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log, bool fmad = false);
 
 }  // namespace sde_host
 
