@@ -140,7 +140,12 @@ class GPUSimpleAVern9(_Alg):
 class ODEProblem:
     """ODEProblem{false}(f, u0, tspan, p): out-of-place problem.  eltype(u0) selects Float64/Float32."""
 
-    def __init__(self, f, u0, tspan, p=None):
+    def __init__(self, f, u0, tspan, p=None, analytic=None):
+        """analytic: optional host callable (u0, p, t) -> u, the counterpart of ODEFunction(f; analytic = ...): when
+        present every solution carries `u_analytic` and `errors` like the reference's epilogue
+        `has_analytic(prob.f) && calculate_solution_errors!(sol; timeseries_errors = true, dense_errors = false)`
+        (src/tsit5/gpuatsit5.jl:141-145, :330-334, src/rk4/gpurk4.jl:92-96, ...)."""
+        self.analytic = analytic
         if not isinstance(f, System):
             raise TypeError("f must be a built-in system or a CudaRHS (no host callables on the GPU path)")
         u0 = np.atleast_1d(np.asarray(u0))
@@ -157,7 +162,7 @@ class ODEProblem:
 
 def remake(prob, u0=None, p=None, tspan=None):
     return ODEProblem(prob.f, prob.u0 if u0 is None else u0, prob.tspan if tspan is None else tspan,
-                      prob.p if p is None else p)
+                      prob.p if p is None else p, analytic=prob.analytic)
 
 
 class EnsembleProblem:
@@ -203,6 +208,25 @@ class ODESolution:
 
     def __len__(self):
         return len(self.t)
+
+    # ---- [EXT] SciMLBase.calculate_solution_errors!(sol; timeseries_errors = true, dense_errors = false), evaluated on
+    # the host on demand: u_analytic[i] = analytic(u0, p, t[i]); errors = (final, l-infinity, l2) of u - u_analytic
+    @property
+    def u_analytic(self):
+        an = self._ens.prob.prob.analytic
+        if an is None:
+            return None
+        u0 = self._ens.u0_soa[:, self._i]
+        p = self._ens.p_soa[:, self._i] if getattr(self._ens, "p_soa", None) is not None else self._ens.prob.prob.p
+        return np.stack([np.atleast_1d(np.asarray(an(u0, p, tk), dtype=self._ens.dtype)) for tk in self.t])
+
+    @property
+    def errors(self):
+        ua = self.u_analytic
+        if ua is None:
+            return None
+        d = np.asarray(self.u, dtype=np.float64) - ua.astype(np.float64)
+        return {"final": float(np.mean(np.abs(d[-1]))), "l∞": float(np.max(np.abs(d))), "l2": float(np.sqrt(np.mean(d * d)))}
 
 
 class EnsembleSolution:
@@ -384,7 +408,7 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, dt=None, abstol=Non
         capacity = int(raw["naccept"].max()) + 1
         raw = solve_arrays(sysm, alg, u0_soa, p_soa, base.tspan, saveat=saveat, save_mode=save_mode, layout=lay,
                            out_capacity=capacity, **common)
-    sol = EnsembleSolution(n_traj=n, dtype=dtype, save_mode=save_mode, layout=lay, u0_soa=u0_soa,
+    sol = EnsembleSolution(n_traj=n, dtype=dtype, save_mode=save_mode, layout=lay, u0_soa=u0_soa, p_soa=p_soa,
                            u_raw=raw["u"], t_shared=raw["t_shared"], t_final=raw["t_final"],
                            t_series=raw["t_series"],
                            t0=_as_T(base.tspan[0], dtype), naccept=raw["naccept"],

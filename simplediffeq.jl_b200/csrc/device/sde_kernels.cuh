@@ -127,21 +127,33 @@ __device__ __forceinline__ void load_problem(const KArgs<T>& a, i64 traj, T* u, 
 //   STAGED = false: direct stores in the layout the launch asked for.  Coalesced for kLayoutSoA
 //            (consecutive lanes -> consecutive addresses).
 //   STAGED = true : kLayoutTrajMajor, fixed step.  Each trajectory owns a contiguous row
-//            out_u[traj][slot][c]; a thread storing its own N values would touch 32 different rows
-//            per instruction.  Instead every warp stages S consecutive slots of its 32 trajectories
-//            in shared memory and then writes 32 contiguous runs of S*N elements with consecutive
-//            lanes on consecutive addresses (full 32-byte sectors except at the run ends, which
-//            the neighbouring runs complete while the line is still in L2).
+//            out_u[traj][slot][c]; a thread storing its own N values per save point would write 32
+//            different rows per instruction, 8 bytes each.  Instead every LANE stages S consecutive slots
+//            of its own trajectory in shared memory and then hands the whole run (S * N elements,
+//            contiguous in its row) to the TMA unit as ONE bulk copy shared -> global
+//            (cp.async.bulk, SASS UBLKCP): no cooperative flush loop, no address arithmetic per element,
+//            and the copy drains while the lane integrates on.  The run length is what DRAM sees
+//            (profiles/r1_scatter_bw_microbench.txt: 360 B runs cap at 2.4 TB/s, 1.5 KB at 3.6 TB/s), so the
+//            stage is as large as shared memory allows at the occupancy the integration needs.
+//            Bulk copies want 16-byte aligned addresses and sizes: rows start at traj * n_out * N elements,
+//            so a lane stages its data at the same offset mod 16 bytes as its row has in global memory and
+//            writes the (at most 16 / sizeof(T) - 1) elements before / after the aligned middle itself.
 // ------------------------------------------------------------------------------------------
+constexpr int stage_gcd(int a, int b) { return b == 0 ? a : stage_gcd(b, a % b); }
+
 template <class T, int N>
 struct StageCfg {
 #ifndef SDE_STAGE_ELEMS_F64
-#define SDE_STAGE_ELEMS_F64 45   // 4 warps x 32 lanes x 45 x 8 B = 46 080 B  (<= 48 KB: no opt-in needed)
-#define SDE_STAGE_ELEMS_F32 93   // 4 warps x 32 lanes x 93 x 4 B = 47 616 B
+#define SDE_STAGE_ELEMS_F64 48    // elements staged per lane: 16 Lorenz slots = 384 B runs, 51 KB per CTA, 4 CTAs per SM.
+#define SDE_STAGE_ELEMS_F32 96    // Larger stages lose more to occupancy than longer runs win (profiles/r2_trajmajor_stage_sweep.txt)
 #endif
+  static constexpr int A = 16 / (int)sizeof(T);                 // elements per 16 bytes
   static constexpr int kElems = (sizeof(T) == 8 ? SDE_STAGE_ELEMS_F64 : SDE_STAGE_ELEMS_F32);
-  static constexpr int S = (kElems / N) > 0 ? (kElems / N) : 1;  // slots staged per flush
-  static constexpr int LS = (S * N) | 1;                      // lane stride, odd: conflict-free for 4- and 8-byte words
+  // S * N is a multiple of A, so every run of a row starts at the same offset mod 16 bytes
+  static constexpr int kStep = A / stage_gcd(A, N);
+  static constexpr int S = ((kElems / N) / kStep) > 0 ? ((kElems / N) / kStep) * kStep : kStep;   // slots staged per flush
+  static constexpr int kRaw = ((S * N + (A - 1)) + (A - 1)) / A * A;    // run + alignment offset, rounded up to 16 bytes
+  static constexpr int LS = ((kRaw / A) % 2 == 0) ? kRaw + A : kRaw;    // lane stride: an odd number of 16-byte units
   static constexpr int kBytesPerWarp = 32 * LS * (int)sizeof(T);
 };
 
@@ -154,66 +166,51 @@ struct SeriesWriter {
   i64 traj;
   bool valid;
   i64 slot;      // next slot to be written by put()
-  T* buf;        // this warp's staging region
+  T* buf;        // this lane's staging region, already shifted by the row's offset mod 16 bytes
   int fill;      // slots currently staged
   i64 slot0;     // slot index of the first staged slot
-  i64 warp_traj0;
-  unsigned lane;
+  int head;      // elements of a run in front of the first 16-byte boundary of the row
+  bool pending;  // a bulk copy may still be reading the staging region
   // direct stores: a running element offset instead of re-deriving (slot * N + c) * ld_out + traj at every put()
   i64 off;       // element offset of the next slot (warp-uniform: lives in the uniform datapath)
 
   __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
-      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0), off(0) {
-    lane = threadIdx.x & 31u;
-    warp_traj0 = traj - lane;
+      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0), head(0), pending(false), off(0) {
     if (STAGED) {
-      buf = reinterpret_cast<T*>(sde_dyn_smem) + (threadIdx.x >> 5) * (32 * Cfg::LS);
+      const int mis = (int)((u64)(traj * a.n_out * N) & (u64)(Cfg::A - 1));   // row start mod 16 bytes, in elements
+      head = (Cfg::A - mis) & (Cfg::A - 1);
+      buf = reinterpret_cast<T*>(sde_dyn_smem) + (i64)threadIdx.x * Cfg::LS + mis;
     }
   }
 
-  template <bool kFull>
+  // hand the staged run of `cnt` slots to the TMA unit (each lane its own row: no warp-level cooperation)
   __device__ __forceinline__ void flush(int cnt) {
-    __syncwarp();
-    const int per = kFull ? Cfg::S * N : cnt * N;    // elements per trajectory in this flush
-    T* const row0 = a.out_u + (warp_traj0 * a.n_out + slot0) * N;   // row of the warp's first trajectory
-    const i64 row_stride = a.n_out * N;
-    const int n_valid = (int)((a.n_traj - warp_traj0) < 32 ? (a.n_traj - warp_traj0) : 32);
-    // each half-warp writes one trajectory's run per pass: 16 consecutive elements per instruction
-    // (128 B for doubles), ceil(per/16) instructions per run, and the row pointer advances by a plain
-    // 64-bit add -- no per-element division / index arithmetic (the element-linear loop this replaces
-    // spent ~12 instructions per 8-byte store, as many as the integration between two flushes)
-    const int half = (int)(lane >> 4), l16 = (int)(lane & 15u);
-    const T* src = buf + half * Cfg::LS + l16;
-    T* dst = row0 + half * row_stride + l16;
-    constexpr int kPasses = (Cfg::S * N + 15) / 16;
-#pragma unroll 4
-    for (int r = half; r < 32; r += 2) {
-      if (r < n_valid) {
-        if (kFull) {
-#pragma unroll
-          for (int j = 0; j < kPasses; ++j)
-            if (j * 16 + 16 <= Cfg::S * N || j * 16 + l16 < Cfg::S * N) dst[j * 16] = src[j * 16];
-        } else {
-          for (int off = l16; off < per; off += 16) dst[off - l16] = src[off - l16];
-        }
-      }
-      src += 2 * Cfg::LS;
-      dst += 2 * row_stride;
-    }
-    __syncwarp();
+    const int per = cnt * N;
+    T* g = a.out_u + (traj * a.n_out + slot0) * N;
+    const int h = head < per ? head : per;
+    const int nb = (per - h) & ~(Cfg::A - 1);
+    for (int e = 0; e < h; ++e) g[e] = buf[e];
+    if (nb > 0) bulk_store_shared_to_global(g + h, buf + h, (unsigned)(nb * (int)sizeof(T)));
+    for (int e = h + nb; e < per; ++e) g[e] = buf[e];
+    bulk_store_commit();
+    pending = true;
     slot0 += cnt;
     fill = 0;
   }
 
-  // all lanes of a warp call put() together with the same slot (fixed-step kernels are uniform)
+  // fixed-step kernels call put() with the same slot in every lane
   __device__ __forceinline__ void put(const T* v) {
     if (STAGED) {
-      T* my = buf + lane * Cfg::LS + fill * N;
+      if (pending && fill == 0) {       // the previous run must have left shared memory before it is overwritten
+        bulk_store_wait_read();
+        pending = false;
+      }
+      T* my = buf + fill * N;
 #pragma unroll
       for (int c = 0; c < N; ++c) my[c] = v[c];
       ++fill;
       ++slot;
-      if (fill == Cfg::S) flush<true>(Cfg::S);
+      if (fill == Cfg::S) flush(Cfg::S);
     } else {
       // strides straight from the kernel parameters (constant-bank operands): no per-thread stride registers
       if (a.layout == kLayoutTrajMajor) {                      // out_u[(traj * n_out + slot) * N + c]
@@ -236,7 +233,10 @@ struct SeriesWriter {
   }
 
   __device__ __forceinline__ void finish() {
-    if (STAGED && fill > 0) flush<false>(fill);
+    if (STAGED) {
+      if (fill > 0) flush(fill);
+      bulk_store_wait_all();          // shared memory must outlive the copies
+    }
   }
 };
 
@@ -257,12 +257,8 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   constexpr bool kEnd = MethodTraits<Method>::kTimeIsStepEnd;
   i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = traj < a.n_traj;
-  if (!STAGED || SAVE == kSaveEndpoint) {
-    if (!valid) return;
-  }
-  // staged series output: every lane of the warp must reach the cooperative flushes, so lanes past
-  // the end integrate a copy of the last trajectory and never store
-  const i64 src = valid ? traj : a.n_traj - 1;
+  if (!valid) return;
+  const i64 src = traj;
 
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
   load_problem<T, N, NP>(a, src, u, p);
@@ -274,35 +270,33 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   int cur = 0;
   if (SAVE == kSaveEveryStep) w.put(u);
   if (SAVE == kSaveAt) {
-    if (a.n_save > 0 && a.plan_step[0] == 0) {   // us[1] = u0 only when tspan[1] == ts[1] exactly (Q8)
+    if (a.n_save > 0 && a.plan_cnt[0] != 0) {   // us[1] = u0 only when tspan[1] == ts[1] exactly (Q8)
       w.put(u);
       cur = 1;
     }
   }
-  // the step of the next save point and its dense-output weights are fetched one save point ahead
-  // (uniform, L1-resident loads whose latency would otherwise sit between the step and its stores)
-  // (the weights only in the staged kernels: shared memory already caps those at 4 CTAs per SM, whereas
-  //  the SoA kernel would lose a CTA per SM to the extra registers -- measured: 90 % -> 81 % of HBM peak)
-  constexpr int kNever = 0x7fffffff;
+  // The number of save points of a step is fetched BEFORE its stages (a uniform, L1-resident load whose latency
+  // then hides behind ~130 FP64 instructions; comparing a prefetched "step of the next save point" after every
+  // save point left that latency exposed -- 40 % of the stall samples of the staged kernel at 8 warps per SM,
+  // profiles/r2_ncu_trajmajor_staged.txt).  The dense-output weights are fetched one save point ahead in the
+  // staged kernels only: shared memory already caps those at few CTAs per SM, whereas the SoA kernel would lose
+  // a CTA per SM to the extra registers (measured in round 1: 90 % -> 81 % of HBM peak).
   constexpr bool kPrefetchB = STAGED;
-  int next_save_step = kNever;
   T b_next[kPrefetchB ? Method::kNB : 1];
-  auto fetch_plan = [&]() {
-    if (SAVE == kSaveAt) {
-      if (cur < a.n_save) {
-        next_save_step = a.plan_step[cur];
-        if (kPrefetchB) {
-#pragma unroll
-          for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
-        }
-      } else {
-        next_save_step = kNever;
-      }
-    }
-  };
-  fetch_plan();
   const T dt = a.dt;
   for (i64 s = 1; s <= a.n_steps; ++s) {
+    int cnt = 0;
+    if (SAVE == kSaveAt) {
+      cnt = a.plan_cnt[s];
+      if (kPrefetchB) {
+        // pull this step's dense-output weights (cnt * kNB elements, a few 128-byte lines) into L1 now: the staged
+        // kernels run few warps per SM next to a large shared-memory carve-out, and an L2 round trip per save point
+        // was the largest single stall (profiles/r2_ncu_trajmajor_staged.txt)
+        const int lines = (cnt * Method::kNB * (int)sizeof(T) + 127) / 128 + 1;
+        const int ln = (int)(threadIdx.x & 31u);
+        if (ln < lines) prefetch_l1(reinterpret_cast<const char*>(a.plan_b + (i64)cur * Method::kNB) + 128 * ln);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < N; ++c) uprev[c] = u[c];
     m.begin_step();
@@ -311,20 +305,27 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     if (!kEnd) t = t + dt;
     if (SAVE == kSaveEveryStep) w.put(u);
     if (SAVE == kSaveAt) {
-      bool prepared = false;
-      while ((i64)next_save_step == s) {
-        if (!prepared) {           // extra stages do not depend on theta: once per step
-          m.template dense_prepare<Q2>(uprev, p, t, dt);   // time base = advanced t (Q3)
-          prepared = true;
-        }
-        T b[Method::kNB];
+      if (cnt > 0) {
+        if (kPrefetchB) {
 #pragma unroll
-        for (int j = 0; j < Method::kNB; ++j) b[j] = kPrefetchB ? b_next[j] : a.plan_b[(i64)cur * Method::kNB + j];
-        ++cur;
-        fetch_plan();
-        T o[N];
-        m.template dense_combine<Q2>(b, dt, uprev, o);
-        w.put(o);
+          for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
+        }
+        m.template dense_prepare<Q2>(uprev, p, t, dt);   // extra stages do not depend on theta: once per step; time base = advanced t (Q3)
+        for (int k = 0; k < cnt; ++k) {
+          T b[Method::kNB];
+#pragma unroll
+          for (int j = 0; j < Method::kNB; ++j) b[j] = kPrefetchB ? b_next[j] : a.plan_b[(i64)cur * Method::kNB + j];
+          ++cur;
+          if (kPrefetchB) {
+            if (k + 1 < cnt) {
+#pragma unroll
+              for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
+            }
+          }
+          T o[N];
+          m.template dense_combine<Q2>(b, dt, uprev, o);
+          w.put(o);
+        }
       }
     }
   }

@@ -94,11 +94,16 @@ int tune_stage_elems() {
   return e ? atoi(e) : 0;
 }
 size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
-  int elems = es == 8 ? 45 : 93;
+  int elems = es == 8 ? 48 : 96;
   if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
-  const int S = std::max(1, elems / n_state);
-  const int LS = (S * n_state) | 1;
-  return (size_t)(block / 32) * 32 * LS * es;
+  const int A = (int)(16 / es);
+  int g = A, r = n_state % A;
+  while (r) { const int t = g % r; g = r; r = t; }          // gcd(A, n_state)
+  const int step = A / g;
+  const int S = std::max(step, (elems / n_state) / step * step);
+  const int raw = ((S * n_state + (A - 1)) + (A - 1)) / A * A;
+  const int LS = ((raw / A) % 2 == 0) ? raw + A : raw;
+  return (size_t)block * LS * es;
 }
 
 struct Compiled {
@@ -287,8 +292,8 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
   char tune_k[96], tune32_k[96];
   {
     const int te = tune_stage_elems();
-    snprintf(tune_k, sizeof tune_k, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 45);
-    snprintf(tune32_k, sizeof tune32_k, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 93);
+    snprintf(tune_k, sizeof tune_k, "-DSDE_STAGE_ELEMS_F64=%d", te > 0 ? te : 48);
+    snprintf(tune32_k, sizeof tune32_k, "-DSDE_STAGE_ELEMS_F32=%d", te > 0 ? te : 96);
   }
   // --fmad=false: only explicit fma() fuses (the reference's @muladd placement; the user's f rounds as written).
   // SDE_COMPAT_FAST_RHS compiles the program with --fmad=true instead.
@@ -472,7 +477,7 @@ struct SolveConsts {
   char* scratch = nullptr;
   const void* tgrid = nullptr;
   const void* saveat = nullptr;
-  const int* plan_step = nullptr;
+  const int* plan_cnt = nullptr;
   const void* plan_b = nullptr;
   sde::u64* queue(int slot) const { return (sde::u64*)(scratch + 16 * slot); }
 };
@@ -494,6 +499,10 @@ int upload_consts_t(const sde_options_t* o, cudaMemPool_t pool, cudaStream_t st,
     if (o->n_steps >= 0x7ffffffeLL) return fail(SDE_ERR_INVALID, "n_steps too large for saveat");
     build_save_plan<T>(o->alg, tg.data(), o->n_steps, (T)o->t0, (T)o->dt, (const T*)o->saveat, o->n_save,
                        &plan_step, &plan_b, &nb);
+    // what the kernels read: the number of save points per step (index 0: the u0 slot)
+    std::vector<int> cnt((size_t)o->n_steps + 1, 0);
+    for (int st_ : plan_step) if (st_ >= 0 && (int64_t)st_ <= o->n_steps) ++cnt[(size_t)st_];
+    plan_step.swap(cnt);
   }
   auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t off_grid = 16 * kQueueSlots;
@@ -514,7 +523,7 @@ int upload_consts_t(const sde_options_t* o, cudaMemPool_t pool, cudaStream_t st,
   if (!plan_step.empty()) {
     SDE_CUDA(cudaMemcpyAsync(c->scratch + off_pstep, plan_step.data(), plan_step.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     SDE_CUDA(cudaMemcpyAsync(c->scratch + off_pb, plan_b.data(), plan_b.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-    c->plan_step = (const int*)(c->scratch + off_pstep);
+    c->plan_cnt = (const int*)(c->scratch + off_pstep);
     c->plan_b = c->scratch + off_pb;
   }
   return SDE_OK;
@@ -554,7 +563,7 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   a.queue = c.queue(qslot);
   a.tgrid = (const T*)c.tgrid;
   a.saveat = (const T*)c.saveat;
-  a.plan_step = c.plan_step;
+  a.plan_cnt = c.plan_cnt;
   a.plan_b = (const T*)c.plan_b;
 
   int dev = 0, sms = 0, per_sm = 0;

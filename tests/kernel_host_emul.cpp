@@ -197,7 +197,10 @@ void run_fixed(const Call& c) {
   std::vector<T> plan_b;
   if (SAVE == sde::kSaveAt) {
     build_plan<T>(c.alg, (const T*)c.tgrid, c.n_steps, (T)c.t0, (T)c.dt, (const T*)c.saveat, c.n_save, &plan_step, &plan_b);
-    a.plan_step = plan_step.data();
+    std::vector<int> cnt((size_t)c.n_steps + 1, 0);        // save points per step, like the launcher (sde_api.cu)
+    for (int st : plan_step) if (st >= 0 && (long long)st <= c.n_steps) ++cnt[(size_t)st];
+    plan_step.swap(cnt);
+    a.plan_cnt = plan_step.data();
     a.plan_b = plan_b.data();
   }
   const long long n_blocks = (c.n_traj + g_lanes - 1) / g_lanes;
