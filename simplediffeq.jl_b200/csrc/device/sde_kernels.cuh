@@ -292,9 +292,11 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
         // pull this step's dense-output weights (cnt * kNB elements, a few 128-byte lines) into L1 now: the staged
         // kernels run few warps per SM next to a large shared-memory carve-out, and an L2 round trip per save point
         // was the largest single stall (profiles/r2_ncu_trajmajor_staged.txt)
+        // (prefetching a step further ahead, or more lines, evicts what the other warps still need: measured slower)
         const int lines = (cnt * Method::kNB * (int)sizeof(T) + 127) / 128 + 1;
         const int ln = (int)(threadIdx.x & 31u);
-        if (ln < lines) prefetch_l1(reinterpret_cast<const char*>(a.plan_b + (i64)cur * Method::kNB) + 128 * ln);
+        const char* line = reinterpret_cast<const char*>(a.plan_b + (i64)cur * Method::kNB) + 128 * ln;
+        if (ln < lines && line < reinterpret_cast<const char*>(a.plan_b + (i64)a.n_save * Method::kNB)) prefetch_l1(line);
       }
     }
 #pragma unroll
