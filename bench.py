@@ -421,7 +421,9 @@ class Bench:
         gbs = n_local * bytes_per_traj(cfg) / (ms_kernel * 1e-3) / 1e9
         if "saveat" in cfg and "instr" not in cfg:
             return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src,
-                    "bytes_per_trajectory": bytes_per_traj(cfg), "traffic": committed_traffic("r1_ncu_config5_traffic.json", n_local)}
+                    "bytes_per_trajectory": bytes_per_traj(cfg),
+                    "traffic": committed_traffic("r2_ncu_config5tm_traffic.json" if cfg.get("layout") == "traj_major" else "r2_ncu_config5_traffic.json", n_local),
+                    "traffic_source": "committed ncu --set full capture of this launch size (profiles/r2_ncu_config5_*.summary.txt), not a live measurement"}
         pipe = self.pipe_peak(cfg)
         r = {"bound": "fp64_pipe" if cfg.get("dtype") != "f32" else "fp32_pipe",
              "achieved": attempts_per_s_gpu * cfg["instr"] / 1e12, "peak": pipe / 1e12, "unit": "T pipe-instr/s",
@@ -627,8 +629,8 @@ def main():
             achieved = acc / (ms_kernel * 1e-3) * cfg["flop"] / 1e12
             rl = {"bound": "fp64_fma" if cfg.get("dtype") != "f32" else "fp32_fma", "achieved": achieved, "peak": 2 * pipe / 1e12,
                   "unit": "TFLOP/s", "frac": achieved / (2 * pipe / 1e12),
-                  "traffic": committed_traffic("r1_ncu_bench_traffic.json", hi - lo) if args.config == "2" else None,
-                  "traffic_source": "committed ncu --set full capture of this launch (profiles/r1_ncu_bench_tsit5_10m.txt), not a live measurement",
+                  "traffic": committed_traffic("r2_ncu_bench_traffic.json", hi - lo) if args.config == "2" else None,
+                  "traffic_source": "committed ncu --set full capture of this launch (profiles/r2_ncu_bench_tsit5_10m.summary.txt), not a live measurement",
                   "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic = %d)" % ((hi - lo) * bytes_per_traj(cfg)),
                   "peak_source": "derived 148 SM x %d FMA/clk x sm_max_mhz of MEASURED_PEAKS.json (no FP64 figure there); tensor cores n/a"
                                  % (FP32_LANES if cfg.get("dtype") == "f32" else FP64_LANES),

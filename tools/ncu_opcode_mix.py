@@ -21,7 +21,7 @@ def main():
     ix = {h: i for i, h in enumerate(hdr)}
     print(rows[0][1] if len(rows[0]) > 1 else "")
     ex = [int(r[ix["Instructions Executed"]]) for r in data]
-    unit = collections.Counter(ex).most_common(1)[0][0]        # execution count shared by the most instructions
+    unit = collections.Counter(e for e in ex if e).most_common(1)[0][0]        # (non-zero) execution count shared by the most instructions
     ops = collections.Counter()
     for r, e in zip(data, ex):
         m = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", r[ix["Source"]])

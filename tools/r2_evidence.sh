@@ -25,4 +25,13 @@ for w in atsit5 vdp; do
 done
 ncu --set full --clock-control none --import-source on -k regex:adaptive_kernel -s 1 -c 1 -o gpurun_out/r2_ncu_avern9_literal_final \
     python tools/prof_adaptive.py avern9 0 > /dev/null 2>&1
-cat gpurun_out/r2_gpu_tests_final.txt; head -c 600 gpurun_out/r2_bench_n1_final.json; echo; ls -la gpurun_out | tail -20
+# summaries are made here (ncu reads its own reports without a GPU too); only two reports travel back (64 MiB cap)
+for r in gpurun_out/*.ncu-rep; do
+  b=${r%.ncu-rep}
+  python tools/ncu_summary.py $r > $b.summary.txt 2>&1
+  python tools/ncu_source_regions.py $r 0.5 > $b.regions.txt 2>&1
+  python tools/ncu_opcode_mix.py $r > $b.opcodes.txt 2>&1
+done
+mkdir -p gpurun_out/keep && mv gpurun_out/r2_ncu_bench_tsit5_10m.ncu-rep gpurun_out/r2_ncu_config5_tm.ncu-rep gpurun_out/keep/
+rm -f gpurun_out/*.ncu-rep && mv gpurun_out/keep/* gpurun_out/ && rmdir gpurun_out/keep
+cat gpurun_out/r2_gpu_tests_final.txt; head -c 600 gpurun_out/r2_bench_n1_final.json; echo; ls -la gpurun_out | tail -40
