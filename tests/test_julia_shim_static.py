@@ -178,3 +178,39 @@ def test_python_ctypes_mirror_matches_the_header_too(sde):
             assert fn.argtypes is not None and len(fn.argtypes) == len(params), name
         if ret == "int":
             assert fn.restype is ctypes.c_int, name
+
+
+def test_shim_block_structure_is_balanced():
+    """No Julia here, so nothing can `include` the shim; this at least keeps it from rotting syntactically: the file is
+    tokenised with the Julia tokenizer of oracle/jlmini (strings, docstrings, comments, symbols) and every (, [, { must
+    close in order, every block opener (module / function / struct / if / for / while / let / do / try / begin / macro /
+    quote) outside brackets must meet its `end`, and the file must end at depth zero.  (`end` and `for` inside brackets
+    or parentheses are an index / a generator, not blocks.)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "jlmini"))
+    import jlmini
+    toks = jlmini.tokenize(SHIM)
+    openers = {"module", "function", "struct", "if", "for", "while", "let", "do", "try", "begin", "macro", "quote"}
+    pairs = {")": "(", "]": "[", "}": "{"}
+    stack, blocks = [], []
+    prev = None
+    for t in toks:
+        if t.kind == "op" and t.val in "([{" and len(t.val) == 1:
+            stack.append((t.val, t.line))
+        elif t.kind == "op" and t.val in pairs:
+            assert stack and stack[-1][0] == pairs[t.val], "unbalanced %r at line %d" % (t.val, t.line)
+            stack.pop()
+        elif t.kind == "kw" and not stack:
+            if t.val in openers and not (t.val == "struct" and prev is not None and prev.kind == "kw" and prev.val == "mutable"
+                                         and blocks and blocks[-1][0] == "mutable"):
+                blocks.append((t.val, t.line))
+            elif t.val == "end":
+                assert blocks, "`end` without an open block at line %d" % t.line
+                blocks.pop()
+        if t.kind != "nl":
+            prev = t
+    assert not stack, "unclosed bracket opened at line %d" % stack[-1][1]
+    assert not blocks, "unclosed `%s` opened at line %d" % blocks[-1]
+    # every exported entry point the shim binds exists in the header (names only; signatures are checked above)
+    for sym in set(re.findall(r"ccall\(\(:(\w+),", SHIM)):
+        assert re.search(r"\b%s\s*\(" % sym, HEADER), sym
