@@ -129,23 +129,27 @@ __device__ __forceinline__ void load_problem(const KArgs<T>& a, i64 traj, T* u, 
 //   STAGED = true : kLayoutTrajMajor, fixed step.  Each trajectory owns a contiguous row
 //            out_u[traj][slot][c]; a thread storing its own N values per save point would write 32
 //            different rows per instruction, 8 bytes each.  Instead every LANE stages S consecutive slots
-//            of its own trajectory in shared memory and then hands the whole run (S * N elements,
-//            contiguous in its row) to the TMA unit as ONE bulk copy shared -> global
-//            (cp.async.bulk, SASS UBLKCP): no cooperative flush loop, no address arithmetic per element,
-//            and the copy drains while the lane integrates on.  The run length is what DRAM sees
-//            (profiles/r1_scatter_bw_microbench.txt: 360 B runs cap at 2.4 TB/s, 1.5 KB at 3.6 TB/s), so the
-//            stage is as large as shared memory allows at the occupancy the integration needs.
+//            of its own trajectory in shared memory; when the stage is full the run (S * N elements,
+//            contiguous in the lane's row) goes to the TMA unit as ONE bulk copy shared -> global
+//            (cp.async.bulk, SASS UBLKCP) and drains while the warp integrates on.  All 32 copies of a warp
+//            are issued by lane 0 from warp-uniform values (first trajectory of the warp, slot counter):
+//            addresses and sizes then live in uniform registers and a copy costs ~6 uniform-datapath
+//            instructions, where a cp.async.bulk with per-lane operands is wrapped by ptxas into a
+//            13-instruction waterfall iteration per lane.
 //            Bulk copies want 16-byte aligned addresses and sizes: rows start at traj * n_out * N elements,
 //            so a lane stages its data at the same offset mod 16 bytes as its row has in global memory and
 //            writes the (at most 16 / sizeof(T) - 1) elements before / after the aligned middle itself.
+//            Shared memory per warp: 32 lanes x LS elements of stage + kRingBytes for the dense-output
+//            weights of the step (fixed_body).  Every lane of the warp must stay alive (lanes without a
+//            trajectory compute a copy of the last one and never write).
 // ------------------------------------------------------------------------------------------
 constexpr int stage_gcd(int a, int b) { return b == 0 ? a : stage_gcd(b, a % b); }
 
 template <class T, int N>
 struct StageCfg {
 #ifndef SDE_STAGE_ELEMS_F64
-#define SDE_STAGE_ELEMS_F64 48    // elements staged per lane: 16 Lorenz slots = 384 B runs, 51 KB per CTA, 4 CTAs per SM.
-#define SDE_STAGE_ELEMS_F32 96    // Larger stages lose more to occupancy than longer runs win (profiles/r2_trajmajor_stage_sweep.txt)
+#define SDE_STAGE_ELEMS_F64 48    // elements staged per lane: 16 Lorenz slots = 384 B runs; 4 CTAs of 4 warps per SM
+#define SDE_STAGE_ELEMS_F32 96
 #endif
   static constexpr int A = 16 / (int)sizeof(T);                 // elements per 16 bytes
   static constexpr int kElems = (sizeof(T) == 8 ? SDE_STAGE_ELEMS_F64 : SDE_STAGE_ELEMS_F32);
@@ -154,7 +158,9 @@ struct StageCfg {
   static constexpr int S = ((kElems / N) / kStep) > 0 ? ((kElems / N) / kStep) * kStep : kStep;   // slots staged per flush
   static constexpr int kRaw = ((S * N + (A - 1)) + (A - 1)) / A * A;    // run + alignment offset, rounded up to 16 bytes
   static constexpr int LS = ((kRaw / A) % 2 == 0) ? kRaw + A : kRaw;    // lane stride: an odd number of 16-byte units
-  static constexpr int kBytesPerWarp = 32 * LS * (int)sizeof(T);
+  static constexpr int kRingBytes = 1024;                               // dense-output weights of a step, per warp
+  static constexpr int kRingElems = kRingBytes / (int)sizeof(T);
+  static constexpr int kBytesPerWarp = 32 * LS * (int)sizeof(T) + kRingBytes;
 };
 
 extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
@@ -166,43 +172,105 @@ struct SeriesWriter {
   i64 traj;
   bool valid;
   i64 slot;      // next slot to be written by put()
-  T* buf;        // this lane's staging region, already shifted by the row's offset mod 16 bytes
+  // staged writer (every value below except buf / head is the same in all lanes of the warp)
+  T* wstage;     // the warp's staging region: lane l owns [l * LS, (l + 1) * LS)
+  T* buf;        // this lane's region, already shifted by the row's offset mod 16 bytes
   int fill;      // slots currently staged
-  i64 slot0;     // slot index of the first staged slot
+  i64 run_off;   // element offset, within a row, of the first staged slot
+  T* grow;       // this lane's row
+  i64 row0;      // element offset of the warp's first row
   int head;      // elements of a run in front of the first 16-byte boundary of the row
-  bool pending;  // a bulk copy may still be reading the staging region
+  bool pending;  // bulk copies may still be reading the staging region
+  unsigned lane;
+  i64 traj0;     // first trajectory of the warp
+  int nrows;     // trajectories of the warp that exist
   // direct stores: a running element offset instead of re-deriving (slot * N + c) * ld_out + traj at every put()
   i64 off;       // element offset of the next slot (warp-uniform: lives in the uniform datapath)
 
   __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
-      : a(a_), traj(traj_), valid(valid_), slot(0), buf(nullptr), fill(0), slot0(0), head(0), pending(false), off(0) {
+      : a(a_), traj(traj_), valid(valid_), slot(0), wstage(nullptr), buf(nullptr), fill(0), run_off(0), grow(nullptr), row0(0), head(0),
+        pending(false), lane(0), traj0(0), nrows(0), off(0) {
     if (STAGED) {
+      lane = threadIdx.x & 31u;
+      // the warp's index as a value ptxas knows to be warp-uniform
+      const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+      traj0 = (i64)blockIdx.x * blockDim.x + (i64)warp * 32;
+      const i64 left = a.n_traj - traj0;
+      const int here = (int)blockDim.x - warp * 32;            // (host emulation: one-lane blocks)
+      nrows = (int)(left < 32 ? (left < 0 ? 0 : left) : 32);
+      if (nrows > here) nrows = here;
+      wstage = reinterpret_cast<T*>(sde_dyn_smem + (size_t)warp * Cfg::kBytesPerWarp);
+      row0 = traj0 * a.n_out * N;
+      grow = a.out_u + traj * a.n_out * N;
       const int mis = (int)((u64)(traj * a.n_out * N) & (u64)(Cfg::A - 1));   // row start mod 16 bytes, in elements
       head = (Cfg::A - mis) & (Cfg::A - 1);
-      buf = reinterpret_cast<T*>(sde_dyn_smem) + (i64)threadIdx.x * Cfg::LS + mis;
+      buf = wstage + (i64)lane * Cfg::LS + mis;
     }
   }
+  // the warp's ring for the dense-output weights of a step (behind the stage, 16-byte aligned)
+  __device__ __forceinline__ T* ring() const { return wstage + 32 * Cfg::LS; }
 
-  // hand the staged run of `cnt` slots to the TMA unit (each lane its own row: no warp-level cooperation)
+  // hand the staged runs of `cnt` slots (the same cnt in every lane) to the TMA unit
   __device__ __forceinline__ void flush(int cnt) {
+    constexpr int A = Cfg::A;
     const int per = cnt * N;
-    T* g = a.out_u + (traj * a.n_out + slot0) * N;
-    const int h = head < per ? head : per;
-    const int nb = (per - h) & ~(Cfg::A - 1);
-    for (int e = 0; e < h; ++e) g[e] = buf[e];
-    if (nb > 0) bulk_store_shared_to_global(g + h, buf + h, (unsigned)(nb * (int)sizeof(T)));
-    for (int e = h + nb; e < per; ++e) g[e] = buf[e];
-    bulk_store_commit();
+    if (valid) {      // the unaligned ends of the lane's own run
+      T* g = grow + run_off;
+      const int h = head < per ? head : per;
+      const int nb = (per - h) & ~(A - 1);
+      for (int e = 0; e < h; ++e) g[e] = buf[e];
+      for (int e = h + nb; e < per; ++e) g[e] = buf[e];
+    }
+    fence_proxy_async_shared();
+    __syncwarp();
+    if (lane == 0) {
+      // The offset of a row mod 16 bytes repeats with a period that divides A rows: head / size / staging offset
+      // are worked out once per phase, the loop only advances two pointers per copy.
+      const i64 rowlen = a.n_out * N;
+      const int mstep = (int)((u64)rowlen & (u64)(A - 1));
+      int m = (int)((u64)row0 & (u64)(A - 1));
+      unsigned goff[A], soff[A], nbytes[A];
+#pragma unroll
+      for (int j = 0; j < A; ++j) {
+        int h = (A - m) & (A - 1);
+        if (h > per) h = per;
+        const int nb = (per - h) & ~(A - 1);
+        goff[j] = (unsigned)(h * (int)sizeof(T));
+        soff[j] = (unsigned)((m + h) * (int)sizeof(T));
+        nbytes[j] = (unsigned)(nb * (int)sizeof(T));
+        m = (m + mstep) & (A - 1);
+      }
+      char* g = reinterpret_cast<char*>(a.out_u + (row0 + run_off));
+      const char* sm = reinterpret_cast<const char*>(wstage);
+      const i64 gstep = rowlen * (i64)sizeof(T);
+      int l = 0;
+      for (; l + A <= nrows; l += A) {          // whole periods: no bound checks
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+          if (nbytes[j] > 0) bulk_store_issue(g + goff[j], sm + soff[j], nbytes[j]);
+          g += gstep;
+          sm += Cfg::LS * (int)sizeof(T);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) {         // the last warp of a ragged ensemble
+        if (l + j < nrows && nbytes[j] > 0) bulk_store_issue(g + goff[j], sm + soff[j], nbytes[j]);
+        g += gstep;
+        sm += Cfg::LS * (int)sizeof(T);
+      }
+      bulk_store_commit();
+    }
     pending = true;
-    slot0 += cnt;
+    run_off += per;
     fill = 0;
   }
 
   // fixed-step kernels call put() with the same slot in every lane
   __device__ __forceinline__ void put(const T* v) {
     if (STAGED) {
-      if (pending && fill == 0) {       // the previous run must have left shared memory before it is overwritten
-        bulk_store_wait_read();
+      if (pending && fill == 0) {       // the previous runs must have left shared memory before they are overwritten
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
         pending = false;
       }
       T* my = buf + fill * N;
@@ -235,7 +303,7 @@ struct SeriesWriter {
   __device__ __forceinline__ void finish() {
     if (STAGED) {
       if (fill > 0) flush(fill);
-      bulk_store_wait_all();          // shared memory must outlive the copies
+      if (lane == 0) bulk_store_wait_all();          // shared memory must outlive the copies
     }
   }
 };
@@ -255,10 +323,18 @@ template <class Sys, class T, class Method, int SAVE, bool Q2, bool STAGED>
 __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP;
   constexpr bool kEnd = MethodTraits<Method>::kTimeIsStepEnd;
+  constexpr bool kStaged = STAGED && SAVE != kSaveEndpoint;
+  constexpr unsigned FULL = 0xffffffffu;
   i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = traj < a.n_traj;
-  if (!valid) return;
-  const i64 src = traj;
+  if (!kStaged) {
+    if (!valid) return;
+  } else {
+    // the staged writer is warp-cooperative: a warp leaves only as a whole, lanes without a trajectory
+    // integrate a copy of the last one (and never write)
+    if (traj - (i64)(threadIdx.x & 31u) >= a.n_traj) return;
+  }
+  const i64 src = valid ? traj : a.n_traj - 1;
 
   T u[N], uprev[N], p[NP > 0 ? NP : 1];
   load_problem<T, N, NP>(a, src, u, p);
@@ -266,8 +342,8 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   Method m;
   T t = a.t0;
   m.seed(u, p, t);
-  SeriesWriter<T, N, STAGED && SAVE != kSaveEndpoint> w(a, traj, valid);
-  int cur = 0;
+  SeriesWriter<T, N, kStaged> w(a, traj, valid);
+  i64 cur = 0;
   if (SAVE == kSaveEveryStep) w.put(u);
   if (SAVE == kSaveAt) {
     if (a.n_save > 0 && a.plan_cnt[0] != 0) {   // us[1] = u0 only when tspan[1] == ts[1] exactly (Q8)
@@ -275,28 +351,54 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
       cur = 1;
     }
   }
-  // The number of save points of a step is fetched BEFORE its stages (a uniform, L1-resident load whose latency
-  // then hides behind ~130 FP64 instructions; comparing a prefetched "step of the next save point" after every
-  // save point left that latency exposed -- 40 % of the stall samples of the staged kernel at 8 warps per SM,
-  // profiles/r2_ncu_trajmajor_staged.txt).  The dense-output weights are fetched one save point ahead in the
-  // staged kernels only: shared memory already caps those at few CTAs per SM, whereas the SoA kernel would lose
-  // a CTA per SM to the extra registers (measured in round 1: 90 % -> 81 % of HBM peak).
-  constexpr bool kPrefetchB = STAGED;
-  T b_next[kPrefetchB ? Method::kNB : 1];
+  // Dense-output weights: plan_b holds NB values per save point with stride NBP (16-byte aligned rows).
+  //   direct kernels: vector loads (LDG.128) right where they are used; the SoA kernel is bound by its stores.
+  //   staged kernels run few warps per SM next to a large shared-memory carve-out, and a global-memory round trip
+  //   per save point was their largest stall (profiles/r2_ncu_trajmajor_staged.txt).  There the warp fetches the
+  //   weights of a whole step BEFORE the step's stages -- each lane two 16-byte pieces, coalesced, ~130 FP64
+  //   instructions ahead of their use -- parks them in its shared-memory ring after the stages, and the save loop
+  //   reads them back as warp-wide broadcasts (LDS.128): no global load, no register rotation in the loop.
+  constexpr int kNB = Method::kNB;
+  constexpr int kNBP = plan_stride<T>(kNB);
+  typedef StageCfg<T, N> SCfg;
+  typedef typename Vec16<T>::type V16;
+  constexpr int kVA = 16 / (int)sizeof(T);
+  constexpr int kRingSaves = SCfg::kRingElems / kNBP;                     // save points per ring load
+  constexpr int kUnitsPerLane = SCfg::kRingBytes / 16 / 32;               // 16-byte pieces per lane and ring load
+  static_assert(!kStaged || SAVE != kSaveAt || kRingSaves >= 1, "weights of one save point must fit the ring");
+  constexpr int kWR = kStaged ? kUnitsPerLane : 1;
+  V16 wreg[kWR];
+  const unsigned lane = threadIdx.x & 31u;
+  // fetch(first, n): this lane's share of the weights of save points [first, first + n) into registers
+  auto fetch = [&](i64 first, int n) {
+    const int units = n * (kNBP / kVA);
+    const V16* gsrc = reinterpret_cast<const V16*>(a.plan_b + first * kNBP);
+#pragma unroll
+    for (int q = 0; q < kWR; ++q) {
+      const int idx = (int)lane + 32 * q;
+      if (idx < units) wreg[q] = gsrc[idx];
+    }
+  };
+  auto stash = [&](int n) {
+    const int units = n * (kNBP / kVA);
+    V16* rdst = reinterpret_cast<V16*>(w.ring());
+#pragma unroll
+    for (int q = 0; q < kWR; ++q) {
+      const int idx = (int)lane + 32 * q;
+      if (idx < units) rdst[idx] = wreg[q];
+    }
+  };
   const T dt = a.dt;
   for (i64 s = 1; s <= a.n_steps; ++s) {
+    // The number of save points of a step is fetched BEFORE its stages (a warp-uniform load whose latency hides
+    // behind the stages; comparing a prefetched "step of the next save point" after every save point left an L1
+    // round trip exposed per save point -- the reason the SoA kernel sat at 0.84-0.90 of the HBM peak in round 1).
     int cnt = 0;
     if (SAVE == kSaveAt) {
       cnt = a.plan_cnt[s];
-      if (kPrefetchB) {
-        // pull this step's dense-output weights (cnt * kNB elements, a few 128-byte lines) into L1 now: the staged
-        // kernels run few warps per SM next to a large shared-memory carve-out, and an L2 round trip per save point
-        // was the largest single stall (profiles/r2_ncu_trajmajor_staged.txt)
-        // (prefetching a step further ahead, or more lines, evicts what the other warps still need: measured slower)
-        const int lines = (cnt * Method::kNB * (int)sizeof(T) + 127) / 128 + 1;
-        const int ln = (int)(threadIdx.x & 31u);
-        const char* line = reinterpret_cast<const char*>(a.plan_b + (i64)cur * Method::kNB) + 128 * ln;
-        if (ln < lines && line < reinterpret_cast<const char*>(a.plan_b + (i64)a.n_save * Method::kNB)) prefetch_l1(line);
+      if (kStaged) {
+        cnt = __shfl_sync(FULL, cnt, 0);          // the same value, but one ptxas knows to be warp-uniform
+        fetch(cur, cnt < kRingSaves ? cnt : kRingSaves);
       }
     }
 #pragma unroll
@@ -308,25 +410,34 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     if (SAVE == kSaveEveryStep) w.put(u);
     if (SAVE == kSaveAt) {
       if (cnt > 0) {
-        if (kPrefetchB) {
-#pragma unroll
-          for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
-        }
         m.template dense_prepare<Q2>(uprev, p, t, dt);   // extra stages do not depend on theta: once per step; time base = advanced t (Q3)
-        for (int k = 0; k < cnt; ++k) {
-          T b[Method::kNB];
-#pragma unroll
-          for (int j = 0; j < Method::kNB; ++j) b[j] = kPrefetchB ? b_next[j] : a.plan_b[(i64)cur * Method::kNB + j];
-          ++cur;
-          if (kPrefetchB) {
-            if (k + 1 < cnt) {
-#pragma unroll
-              for (int j = 0; j < Method::kNB; ++j) b_next[j] = a.plan_b[(i64)cur * Method::kNB + j];
+        if (kStaged) {
+          for (int done = 0; done < cnt;) {
+            const int nb = (cnt - done) < kRingSaves ? (cnt - done) : kRingSaves;
+            if (done > 0) fetch(cur, nb);         // a step with more save points than the ring holds: exposed, rare
+            __syncwarp();                         // every lane is done with the previous contents of the ring
+            stash(nb);
+            __syncwarp();
+            const T* rb = w.ring();
+            for (int k = 0; k < nb; ++k) {
+              T b[kNB];
+              load_weights<T, kNB>(rb + k * kNBP, b);
+              T o[N];
+              m.template dense_combine<Q2>(b, dt, uprev, o);
+              w.put(o);
             }
+            done += nb;
+            cur += nb;
           }
-          T o[N];
-          m.template dense_combine<Q2>(b, dt, uprev, o);
-          w.put(o);
+        } else {
+          for (int k = 0; k < cnt; ++k) {
+            T b[kNB];
+            load_weights<T, kNB>(a.plan_b + cur * kNBP, b);
+            ++cur;
+            T o[N];
+            m.template dense_combine<Q2>(b, dt, uprev, o);
+            w.put(o);
+          }
         }
       }
     }

@@ -103,7 +103,8 @@ size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
   const int S = std::max(step, (elems / n_state) / step * step);
   const int raw = ((S * n_state + (A - 1)) + (A - 1)) / A * A;
   const int LS = ((raw / A) % 2 == 0) ? raw + A : raw;
-  return (size_t)block * LS * es;
+  // per warp: 32 lanes x LS elements of stage + the 1 KB ring of dense-output weights (StageCfg::kBytesPerWarp)
+  return (size_t)(block / 32) * ((size_t)32 * LS * es + 1024);
 }
 
 struct Compiled {
@@ -405,9 +406,13 @@ void build_save_plan(int alg, const T* tgrid, int64_t n_steps, T t0, T dt, const
     case SDE_ALG_VERN7: poly = &sde_host::kVern7Poly[0][0]; len = sde_host::kVern7Len; nb = sde_host::kVern7NB; deg = sde_host::kVern7Deg; break;
     default: poly = &sde_host::kVern9Poly[0][0]; len = sde_host::kVern9Len; nb = sde_host::kVern9NB; deg = sde_host::kVern9Deg; break;
   }
-  *nb_out = nb;
+  // rows of nbp = nb rounded up to 16 bytes: the kernels read a save point's weights with 16-byte vector loads
+  // (sde::plan_stride)
+  const int va = (int)(16 / sizeof(T));
+  const int nbp = (nb + va - 1) / va * va;
+  *nb_out = nbp;
   step->assign((size_t)n_save, (int)std::min<int64_t>(n_steps + 1, 0x7fffffff));   // "never reached"
-  b->assign((size_t)n_save * nb, (T)0);
+  b->assign((size_t)n_save * nbp, (T)0);
   int64_t cur = 0;
   if (n_save > 0 && t0 == saveat[0]) { (*step)[0] = 0; cur = 1; }
   for (int64_t s = 1; s <= n_steps && cur < n_save; ++s) {
@@ -421,7 +426,7 @@ void build_save_plan(int alg, const T* tgrid, int64_t n_steps, T t0, T dt, const
         const double* c = poly + (size_t)j * deg;
         T acc = (T)c[len[j] - 1];
         for (int d = len[j] - 2; d >= 0; --d) acc = std::fma(th, acc, (T)c[d]);
-        (*b)[(size_t)cur * nb + j] = acc;
+        (*b)[(size_t)cur * nbp + j] = acc;
       }
       (*step)[(size_t)cur] = (int)s;
       ++cur;

@@ -166,8 +166,9 @@ void build_plan(int alg, const T* tgrid, long long n_steps, T t0, T dt, const T*
   if (alg == sde::kTsit5) { poly = &sde_host::kTsit5Poly[0][0]; len = sde_host::kTsit5Len; nb = sde_host::kTsit5NB; deg = sde_host::kTsit5Deg; }
   else if (alg == sde::kVern7) { poly = &sde_host::kVern7Poly[0][0]; len = sde_host::kVern7Len; nb = sde_host::kVern7NB; deg = sde_host::kVern7Deg; }
   else { poly = &sde_host::kVern9Poly[0][0]; len = sde_host::kVern9Len; nb = sde_host::kVern9NB; deg = sde_host::kVern9Deg; }
+  const int va = (int)(16 / sizeof(T)), nbp = (nb + va - 1) / va * va;   // row stride of the weights (sde::plan_stride)
   step->assign((size_t)n_save, (int)(n_steps + 1));      // "never reached"
-  b->assign((size_t)n_save * nb, (T)0);
+  b->assign((size_t)n_save * nbp + va, (T)0);
   long long cur = 0;
   if (n_save > 0 && t0 == saveat[0]) { (*step)[0] = 0; cur = 1; }
   for (long long s = 1; s <= n_steps && cur < n_save; ++s) {
@@ -181,7 +182,7 @@ void build_plan(int alg, const T* tgrid, long long n_steps, T t0, T dt, const T*
         const double* c = poly + (size_t)j * deg;
         T acc = (T)c[len[j] - 1];
         for (int d = len[j] - 2; d >= 0; --d) acc = std::fma(th, acc, (T)c[d]);
-        (*b)[(size_t)cur * nb + j] = acc;
+        (*b)[(size_t)cur * nbp + j] = acc;
       }
       (*step)[(size_t)cur] = (int)s;
       ++cur;
