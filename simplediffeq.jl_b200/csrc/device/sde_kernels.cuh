@@ -128,39 +128,43 @@ __device__ __forceinline__ void load_problem(const KArgs<T>& a, i64 traj, T* u, 
 //            (consecutive lanes -> consecutive addresses).
 //   STAGED = true : kLayoutTrajMajor, fixed step.  Each trajectory owns a contiguous row
 //            out_u[traj][slot][c]; a thread storing its own N values per save point would write 32
-//            different rows per instruction, 8 bytes each.  Instead every LANE stages S consecutive slots
-//            of its own trajectory in shared memory; when the stage is full the run (S * N elements,
-//            contiguous in the lane's row) goes to the TMA unit as ONE bulk copy shared -> global
-//            (cp.async.bulk, SASS UBLKCP) and drains while the warp integrates on.  All 32 copies of a warp
-//            are issued by lane 0 from warp-uniform values (first trajectory of the warp, slot counter):
-//            addresses and sizes then live in uniform registers and a copy costs ~6 uniform-datapath
-//            instructions, where a cp.async.bulk with per-lane operands is wrapped by ptxas into a
-//            13-instruction waterfall iteration per lane.
-//            Bulk copies want 16-byte aligned addresses and sizes: rows start at traj * n_out * N elements,
-//            so a lane stages its data at the same offset mod 16 bytes as its row has in global memory and
-//            writes the (at most 16 / sizeof(T) - 1) elements before / after the aligned middle itself.
+//            different rows per instruction, 8 bytes each.  Instead every LANE stages its row's byte stream in
+//            shared memory, and the warp writes it out in WHOLE 128-BYTE LINES of global memory:
+//              * a lane's staging region is congruent with global memory mod 128 bytes (region byte 0 = the line
+//                that holds the first unwritten byte of the row), so a line of the row is a line of the region;
+//              * as soon as K0 lines are complete in every lane (a warp-uniform count: fixed-step lanes write in
+//                lockstep) the warp copies them row after row -- lane q moves the q-th 16-byte piece (LDS.128 ->
+//                STG.128; with K0 = 2 a pass covers two rows) -- and every lane slides what is left of its region
+//                (less than 128 bytes + one slot) to the front;
+//              * only the first line of a row (shared with the previous row) and the bytes left at the end are
+//                written by their owner lane with scalar stores.
+//            Why lines: rows start at every multiple of 8 bytes mod 128 (24 024-byte rows), and runs cut at slot
+//            boundaries leave a partially written sector / line at both ends of every run, which L2 hands to DRAM
+//            separately.  Pure-store microbenchmark with the real row length (tools/micro/tm_store_bw.cu,
+//            profiles/r2_tm_store_microbench.txt): slot-aligned 384-byte runs 3.1-3.4 TB/s, whole lines 4.5-4.7 TB/s.
 //            Shared memory per warp: 32 lanes x LS elements of stage + kRingBytes for the dense-output
 //            weights of the step (fixed_body).  Every lane of the warp must stay alive (lanes without a
 //            trajectory compute a copy of the last one and never write).
 // ------------------------------------------------------------------------------------------
-constexpr int stage_gcd(int a, int b) { return b == 0 ? a : stage_gcd(b, a % b); }
-
 template <class T, int N>
 struct StageCfg {
 #ifndef SDE_STAGE_ELEMS_F64
-#define SDE_STAGE_ELEMS_F64 48    // elements staged per lane: 16 Lorenz slots = 384 B runs; 4 CTAs of 4 warps per SM
+#define SDE_STAGE_ELEMS_F64 48    // staging capacity per lane in elements (+ 16 bytes): 400 B, 4 CTAs of 4 warps per SM
 #define SDE_STAGE_ELEMS_F32 96
 #endif
-  static constexpr int A = 16 / (int)sizeof(T);                 // elements per 16 bytes
-  static constexpr int kElems = (sizeof(T) == 8 ? SDE_STAGE_ELEMS_F64 : SDE_STAGE_ELEMS_F32);
-  // S * N is a multiple of A, so every run of a row starts at the same offset mod 16 bytes
-  static constexpr int kStep = A / stage_gcd(A, N);
-  static constexpr int S = ((kElems / N) / kStep) > 0 ? ((kElems / N) / kStep) * kStep : kStep;   // slots staged per flush
-  static constexpr int kRaw = ((S * N + (A - 1)) + (A - 1)) / A * A;    // run + alignment offset, rounded up to 16 bytes
-  static constexpr int LS = ((kRaw / A) % 2 == 0) ? kRaw + A : kRaw;    // lane stride: an odd number of 16-byte units
+  static constexpr int kSz = (int)sizeof(T);
+  static constexpr int kLineE = 128 / kSz;                      // elements per 128-byte line
+  static constexpr int kElems = (kSz == 8 ? SDE_STAGE_ELEMS_F64 : SDE_STAGE_ELEMS_F32);
+  // worst case before a flush: (128 - sz) bytes of line offset + K0 lines + one slot that just crossed the boundary
+  static constexpr int kNeed = (128 - kSz) + 128 + (N * kSz - kSz);
+  static constexpr int kWant = kElems * kSz + 16;
+  static constexpr int kRawB = ((kWant > kNeed ? kWant : kNeed) + 15) / 16 * 16;
+  static constexpr int kCapB = ((kRawB / 16) % 2 == 0) ? kRawB + 16 : kRawB;   // lane stride: an odd number of 16-byte units
+  static constexpr int LS = kCapB / kSz;
+  static constexpr int K0 = (kCapB - (128 - kSz) - (N * kSz - kSz)) / 128;     // lines per flush (>= 1)
   static constexpr int kRingBytes = 1024;                               // dense-output weights of a step, per warp
-  static constexpr int kRingElems = kRingBytes / (int)sizeof(T);
-  static constexpr int kBytesPerWarp = 32 * LS * (int)sizeof(T) + kRingBytes;
+  static constexpr int kRingElems = kRingBytes / kSz;
+  static constexpr int kBytesPerWarp = 32 * kCapB + kRingBytes;
 };
 
 extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
@@ -172,113 +176,116 @@ struct SeriesWriter {
   i64 traj;
   bool valid;
   i64 slot;      // next slot to be written by put()
-  // staged writer (every value below except buf / head is the same in all lanes of the warp)
-  T* wstage;     // the warp's staging region: lane l owns [l * LS, (l + 1) * LS)
-  T* buf;        // this lane's region, already shifted by the row's offset mod 16 bytes
-  int fill;      // slots currently staged
-  i64 run_off;   // element offset, within a row, of the first staged slot
-  T* grow;       // this lane's row
-  i64 row0;      // element offset of the warp's first row
-  int head;      // elements of a run in front of the first 16-byte boundary of the row
-  bool pending;  // bulk copies may still be reading the staging region
+  // staged writer
+  unsigned char* wstage;   // the warp's staging region: lane l owns bytes [l * kCapB, (l + 1) * kCapB)
+  T* buf;        // this lane's region
+  int wpos;      // element index in buf of the next value            (lane specific: includes the row's line offset)
+  int wb;        // elements staged beyond the flushed lines by a row that starts on a line boundary (warp uniform)
+  i64 lines;     // lines of the rows written so far                  (warp uniform)
+  char* gline;   // global address of the line that holds the start of this lane's row
   unsigned lane;
-  i64 traj0;     // first trajectory of the warp
-  int nrows;     // trajectories of the warp that exist
+  u64 gbase0;    // byte address of the warp's first row               (warp uniform)
+  int nrows;     // trajectories of the warp that exist                (warp uniform)
   // direct stores: a running element offset instead of re-deriving (slot * N + c) * ld_out + traj at every put()
   i64 off;       // element offset of the next slot (warp-uniform: lives in the uniform datapath)
 
   __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
-      : a(a_), traj(traj_), valid(valid_), slot(0), wstage(nullptr), buf(nullptr), fill(0), run_off(0), grow(nullptr), row0(0), head(0),
-        pending(false), lane(0), traj0(0), nrows(0), off(0) {
+      : a(a_), traj(traj_), valid(valid_), slot(0), wstage(nullptr), buf(nullptr), wpos(0), wb(0), lines(0),
+        gline(nullptr), lane(0), gbase0(0), nrows(0), off(0) {
     if (STAGED) {
       lane = threadIdx.x & 31u;
       // the warp's index as a value ptxas knows to be warp-uniform
       const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-      traj0 = (i64)blockIdx.x * blockDim.x + (i64)warp * 32;
+      const i64 traj0 = (i64)blockIdx.x * blockDim.x + (i64)warp * 32;
       const i64 left = a.n_traj - traj0;
       const int here = (int)blockDim.x - warp * 32;            // (host emulation: one-lane blocks)
       nrows = (int)(left < 32 ? (left < 0 ? 0 : left) : 32);
       if (nrows > here) nrows = here;
-      wstage = reinterpret_cast<T*>(sde_dyn_smem + (size_t)warp * Cfg::kBytesPerWarp);
-      row0 = traj0 * a.n_out * N;
-      grow = a.out_u + traj * a.n_out * N;
-      const int mis = (int)((u64)(traj * a.n_out * N) & (u64)(Cfg::A - 1));   // row start mod 16 bytes, in elements
-      head = (Cfg::A - mis) & (Cfg::A - 1);
-      buf = wstage + (i64)lane * Cfg::LS + mis;
+      wstage = sde_dyn_smem + (size_t)warp * Cfg::kBytesPerWarp;
+      buf = reinterpret_cast<T*>(wstage + (size_t)lane * Cfg::kCapB);
+      const i64 rowbytes = a.n_out * N * (i64)sizeof(T);
+      gbase0 = (u64)a.out_u + (u64)(traj0 * rowbytes);
+      const u64 mine = (u64)a.out_u + (u64)(traj * rowbytes);
+      gline = reinterpret_cast<char*>(mine & ~(u64)127);
+      wpos = (int)(mine & (u64)127) / Cfg::kSz;
     }
   }
   // the warp's ring for the dense-output weights of a step (behind the stage, 16-byte aligned)
-  __device__ __forceinline__ T* ring() const { return wstage + 32 * Cfg::LS; }
+  __device__ __forceinline__ T* ring() const { return reinterpret_cast<T*>(wstage + 32 * Cfg::kCapB); }
 
-  // hand the staged runs of `cnt` slots (the same cnt in every lane) to the TMA unit
-  __device__ __forceinline__ void flush(int cnt) {
-    constexpr int A = Cfg::A;
-    const int per = cnt * N;
-    if (valid) {      // the unaligned ends of the lane's own run
-      T* g = grow + run_off;
-      const int h = head < per ? head : per;
-      const int nb = (per - h) & ~(A - 1);
-      for (int e = 0; e < h; ++e) g[e] = buf[e];
-      for (int e = h + nb; e < per; ++e) g[e] = buf[e];
-    }
-    fence_proxy_async_shared();
-    __syncwarp();
-    if (lane == 0) {
-      // The offset of a row mod 16 bytes repeats with a period that divides A rows: head / size / staging offset
-      // are worked out once per phase, the loop only advances two pointers per copy.
-      const i64 rowlen = a.n_out * N;
-      const int mstep = (int)((u64)rowlen & (u64)(A - 1));
-      int m = (int)((u64)row0 & (u64)(A - 1));
-      unsigned goff[A], soff[A], nbytes[A];
+  // the warp writes lines [first, K) of every lane's region to the rows (all arguments warp uniform)
+  __device__ __forceinline__ void copy_lines(int first, int K) {
+    constexpr int P = Cfg::K0 * 8;                       // 16-byte pieces per row in the common case
+    constexpr int RP = 32 / P > 0 ? 32 / P : 1;          // rows per pass of the warp
+    const i64 rowbytes = a.n_out * N * (i64)sizeof(T);
+    const u64 foff = (u64)lines * 128u;
+    if (first == 0 && K == Cfg::K0 && P <= 32 && nrows == 32) {
+      // common case: K0 whole lines per row, RP rows per pass, four passes in flight
+      typedef typename Vec16<T>::type V16;
+      const unsigned rr = lane / P, q = lane % P;        // (P is a power of two or 24: folded at compile time)
+      const bool act = rr < (unsigned)RP;
+      const unsigned char* sp = wstage + rr * Cfg::kCapB + q * 16u;
+      u64 brow = gbase0 + (u64)rr * (u64)rowbytes;
+      const u64 bstep = (u64)RP * (u64)rowbytes;
+      constexpr int kBatch = 4;
+      static_assert((32 / RP) % kBatch == 0, "passes per flush must be a multiple of the batch");
+      for (int r0 = 0; r0 < 32; r0 += RP * kBatch) {
+        V16 v[kBatch];
 #pragma unroll
-      for (int j = 0; j < A; ++j) {
-        int h = (A - m) & (A - 1);
-        if (h > per) h = per;
-        const int nb = (per - h) & ~(A - 1);
-        goff[j] = (unsigned)(h * (int)sizeof(T));
-        soff[j] = (unsigned)((m + h) * (int)sizeof(T));
-        nbytes[j] = (unsigned)(nb * (int)sizeof(T));
-        m = (m + mstep) & (A - 1);
-      }
-      char* g = reinterpret_cast<char*>(a.out_u + (row0 + run_off));
-      const char* sm = reinterpret_cast<const char*>(wstage);
-      const i64 gstep = rowlen * (i64)sizeof(T);
-      int l = 0;
-      for (; l + A <= nrows; l += A) {          // whole periods: no bound checks
+        for (int i = 0; i < kBatch; ++i)
+          if (act) v[i] = load16<T>(sp + (size_t)(r0 + i * RP) * Cfg::kCapB);
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
-          if (nbytes[j] > 0) bulk_store_issue(g + goff[j], sm + soff[j], nbytes[j]);
-          g += gstep;
-          sm += Cfg::LS * (int)sizeof(T);
+        for (int i = 0; i < kBatch; ++i) {
+          if (act) store16<T>(reinterpret_cast<char*>((brow & ~(u64)127) + foff + q * 16u), v[i]);
+          brow += bstep;
         }
       }
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) {         // the last warp of a ragged ensemble
-        if (l + j < nrows && nbytes[j] > 0) bulk_store_issue(g + goff[j], sm + soff[j], nbytes[j]);
-        g += gstep;
-        sm += Cfg::LS * (int)sizeof(T);
+    } else {
+      u64 brow = gbase0;
+      const unsigned char* sp = wstage;
+      for (int r = 0; r < nrows; ++r) {
+        char* g = reinterpret_cast<char*>((brow & ~(u64)127) + foff);
+        for (unsigned q = (unsigned)first * 128u + lane * 16u; q < (unsigned)K * 128u; q += 512u) copy16<T>(g + q, sp + q);
+        brow += (u64)rowbytes;
+        sp += Cfg::kCapB;
       }
-      bulk_store_commit();
     }
-    pending = true;
-    run_off += per;
-    fill = 0;
+  }
+
+  // all lanes hold at least K = wb / kLineE complete lines: write them, keep the rest
+  __device__ __forceinline__ void flush_lines() {
+    const int K = wb / Cfg::kLineE;
+    __syncwarp();
+    if (lines == 0) {
+      // line 0 is shared with the previous row: the owner writes its part
+      if (valid) {
+        const int e0 = wpos - wb;                      // the row's offset in its first line (wpos = offset + wb throughout)
+        T* g = reinterpret_cast<T*>(gline);
+        for (int e = e0; e < Cfg::kLineE; ++e) g[e] = buf[e];
+      }
+      copy_lines(1, K);
+    } else {
+      copy_lines(0, K);
+    }
+    __syncwarp();
+    // slide the unwritten rest of the region to the front (16-byte pieces; at most one line + one slot)
+    const int keep = wpos - K * Cfg::kLineE;                        // elements (lane specific)
+    for (int e = 0; e < keep; e += 16 / Cfg::kSz) copy16<T>(buf + e, buf + K * Cfg::kLineE + e);
+    wpos = keep;
+    wb -= K * Cfg::kLineE;
+    lines += K;
   }
 
   // fixed-step kernels call put() with the same slot in every lane
   __device__ __forceinline__ void put(const T* v) {
     if (STAGED) {
-      if (pending && fill == 0) {       // the previous runs must have left shared memory before they are overwritten
-        if (lane == 0) bulk_store_wait_read();
-        __syncwarp();
-        pending = false;
-      }
-      T* my = buf + fill * N;
+      T* my = buf + wpos;
 #pragma unroll
       for (int c = 0; c < N; ++c) my[c] = v[c];
-      ++fill;
+      wpos += N;
+      wb += N;
       ++slot;
-      if (fill == Cfg::S) flush(Cfg::S);
+      if (wb >= Cfg::K0 * Cfg::kLineE) flush_lines();
     } else {
       // strides straight from the kernel parameters (constant-bank operands): no per-thread stride registers
       if (a.layout == kLayoutTrajMajor) {                      // out_u[(traj * n_out + slot) * N + c]
@@ -300,10 +307,14 @@ struct SeriesWriter {
     }
   }
 
+  // the end of the rows: what is still staged goes out by scalar stores of the owner lanes
   __device__ __forceinline__ void finish() {
     if (STAGED) {
-      if (fill > 0) flush(fill);
-      if (lane == 0) bulk_store_wait_all();          // shared memory must outlive the copies
+      if (valid) {
+        T* g = reinterpret_cast<T*>(gline + lines * 128);
+        const int e0 = (lines == 0) ? (wpos - wb) : 0;
+        for (int e = e0; e < wpos; ++e) g[e] = buf[e];
+      }
     }
   }
 };
@@ -355,9 +366,12 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   //   direct kernels: vector loads (LDG.128) right where they are used; the SoA kernel is bound by its stores.
   //   staged kernels run few warps per SM next to a large shared-memory carve-out, and a global-memory round trip
   //   per save point was their largest stall (profiles/r2_ncu_trajmajor_staged.txt).  There the warp fetches the
-  //   weights of a whole step BEFORE the step's stages -- each lane two 16-byte pieces, coalesced, ~130 FP64
-  //   instructions ahead of their use -- parks them in its shared-memory ring after the stages, and the save loop
-  //   reads them back as warp-wide broadcasts (LDS.128): no global load, no register rotation in the loop.
+  //   weights of a step ONE STEP AHEAD -- each lane two 16-byte pieces, coalesced, into registers at the top of the
+  //   previous step (with ~100 GB of output streaming through L2 the table does not stay cached: a fetch issued
+  //   only before the step's own stages still showed up as 16 % of the stall samples) -- parks them in its
+  //   shared-memory ring at the top of the step, and the save loop reads them back as warp-wide broadcasts
+  //   (LDS.128): no global load, no register rotation in the loop.  Save points beyond the ring's capacity
+  //   (more than kRingSaves in one step) read their weights from global memory.
   constexpr int kNB = Method::kNB;
   constexpr int kNBP = plan_stride<T>(kNB);
   typedef StageCfg<T, N> SCfg;
@@ -365,8 +379,9 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   constexpr int kVA = 16 / (int)sizeof(T);
   constexpr int kRingSaves = SCfg::kRingElems / kNBP;                     // save points per ring load
   constexpr int kUnitsPerLane = SCfg::kRingBytes / 16 / 32;               // 16-byte pieces per lane and ring load
-  static_assert(!kStaged || SAVE != kSaveAt || kRingSaves >= 1, "weights of one save point must fit the ring");
-  constexpr int kWR = kStaged ? kUnitsPerLane : 1;
+  constexpr bool kRing = kStaged && SAVE == kSaveAt;
+  static_assert(!kRing || kRingSaves >= 1, "weights of one save point must fit the ring");
+  constexpr int kWR = kRing ? kUnitsPerLane : 1;
   V16 wreg[kWR];
   const unsigned lane = threadIdx.x & 31u;
   // fetch(first, n): this lane's share of the weights of save points [first, first + n) into registers
@@ -389,16 +404,32 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     }
   };
   const T dt = a.dt;
+  // The number of save points of a step is known BEFORE its stages (a warp-uniform load whose latency hides
+  // behind the stages; comparing a prefetched "step of the next save point" after every save point left an L1
+  // round trip exposed per save point -- the reason the SoA kernel sat at 0.84-0.90 of the HBM peak in round 1).
+  // Staged kernels run the schedule two steps ahead: cnt_next (step s + 1) sizes the weight fetch.
+  int cnt_cur = 0, cnt_next = 0;
+  if (kRing) {
+    if (a.n_steps >= 1) {
+      cnt_cur = __shfl_sync(FULL, a.plan_cnt[1], 0);     // the same value, but one ptxas knows to be warp-uniform
+      fetch(cur, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
+    }
+    if (a.n_steps >= 2) cnt_next = a.plan_cnt[2];
+  }
   for (i64 s = 1; s <= a.n_steps; ++s) {
-    // The number of save points of a step is fetched BEFORE its stages (a warp-uniform load whose latency hides
-    // behind the stages; comparing a prefetched "step of the next save point" after every save point left an L1
-    // round trip exposed per save point -- the reason the SoA kernel sat at 0.84-0.90 of the HBM peak in round 1).
     int cnt = 0;
     if (SAVE == kSaveAt) {
-      cnt = a.plan_cnt[s];
-      if (kStaged) {
-        cnt = __shfl_sync(FULL, cnt, 0);          // the same value, but one ptxas knows to be warp-uniform
-        fetch(cur, cnt < kRingSaves ? cnt : kRingSaves);
+      if (kRing) {
+        cnt = cnt_cur;
+        const int nring = cnt < kRingSaves ? cnt : kRingSaves;
+        __syncwarp();                             // every lane is done with the previous contents of the ring
+        stash(nring);
+        __syncwarp();
+        cnt_cur = __shfl_sync(FULL, cnt_next, 0);
+        fetch(cur + cnt, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
+        cnt_next = (s + 2 <= a.n_steps) ? a.plan_cnt[s + 2] : 0;
+      } else {
+        cnt = a.plan_cnt[s];
       }
     }
 #pragma unroll
@@ -411,34 +442,26 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     if (SAVE == kSaveAt) {
       if (cnt > 0) {
         m.template dense_prepare<Q2>(uprev, p, t, dt);   // extra stages do not depend on theta: once per step; time base = advanced t (Q3)
-        if (kStaged) {
-          for (int done = 0; done < cnt;) {
-            const int nb = (cnt - done) < kRingSaves ? (cnt - done) : kRingSaves;
-            if (done > 0) fetch(cur, nb);         // a step with more save points than the ring holds: exposed, rare
-            __syncwarp();                         // every lane is done with the previous contents of the ring
-            stash(nb);
-            __syncwarp();
-            const T* rb = w.ring();
-            for (int k = 0; k < nb; ++k) {
-              T b[kNB];
-              load_weights<T, kNB>(rb + k * kNBP, b);
-              T o[N];
-              m.template dense_combine<Q2>(b, dt, uprev, o);
-              w.put(o);
-            }
-            done += nb;
-            cur += nb;
-          }
-        } else {
-          for (int k = 0; k < cnt; ++k) {
+        int k = 0;
+        if (kRing) {
+          const int nring = cnt < kRingSaves ? cnt : kRingSaves;
+          const T* rb = w.ring();
+          for (; k < nring; ++k) {
             T b[kNB];
-            load_weights<T, kNB>(a.plan_b + cur * kNBP, b);
-            ++cur;
+            load_weights<T, kNB>(rb + k * kNBP, b);
             T o[N];
             m.template dense_combine<Q2>(b, dt, uprev, o);
             w.put(o);
           }
         }
+        for (; k < cnt; ++k) {
+          T b[kNB];
+          load_weights<T, kNB>(a.plan_b + (cur + k) * kNBP, b);
+          T o[N];
+          m.template dense_combine<Q2>(b, dt, uprev, o);
+          w.put(o);
+        }
+        cur += cnt;
       }
     }
   }

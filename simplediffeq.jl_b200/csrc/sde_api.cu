@@ -96,15 +96,14 @@ int tune_stage_elems() {
 size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
   int elems = es == 8 ? 48 : 96;
   if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
-  const int A = (int)(16 / es);
-  int g = A, r = n_state % A;
-  while (r) { const int t = g % r; g = r; r = t; }          // gcd(A, n_state)
-  const int step = A / g;
-  const int S = std::max(step, (elems / n_state) / step * step);
-  const int raw = ((S * n_state + (A - 1)) + (A - 1)) / A * A;
-  const int LS = ((raw / A) % 2 == 0) ? raw + A : raw;
-  // per warp: 32 lanes x LS elements of stage + the 1 KB ring of dense-output weights (StageCfg::kBytesPerWarp)
-  return (size_t)(block / 32) * ((size_t)32 * LS * es + 1024);
+  // StageCfg::kCapB: the configured capacity, at least one line + line offset + one slot, an odd number of 16-byte units
+  const int sz = (int)es;
+  const int need = (128 - sz) + 128 + (n_state * sz - sz);
+  const int want = elems * sz + 16;
+  const int raw = (std::max(want, need) + 15) / 16 * 16;
+  const int cap = ((raw / 16) % 2 == 0) ? raw + 16 : raw;
+  // per warp: 32 lane regions + the 1 KB ring of dense-output weights (StageCfg::kBytesPerWarp)
+  return (size_t)(block / 32) * ((size_t)32 * cap + 1024);
 }
 
 struct Compiled {
@@ -225,9 +224,9 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
              kBlock, method_name(alg), save, alg == SDE_ALG_AVERN9 ? "true" : "false", strict ? "true" : "false");
   } else {
     snprintf(buf, sizeof buf,
-             "extern \"C\" __global__ void __launch_bounds__(%d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
+             "extern \"C\" __global__ void __launch_bounds__(%d, %d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
              "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
-             kBlock, method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
+             kBlock, (staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1, method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
   }
   s += buf;
   return s;
@@ -298,12 +297,25 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
   }
   // --fmad=false: only explicit fma() fuses (the reference's @muladd placement; the user's f rounds as written).
   // SDE_COMPAT_FAST_RHS compiles the program with --fmad=true instead.
-  const char* key_opts[] = {"--gpu-architecture=sm_100a", fmad ? "--fmad=true" : "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
+  // SDE_TUNE_DEFINES="-DNAME=value ..." (development, NVRTC systems only): extra macro definitions for A/B runs of
+  // kernel variants in one process
+  std::vector<std::string> extra;
+  if (const char* e = getenv("SDE_TUNE_DEFINES")) {
+    std::string cur_opt;
+    for (const char* c = e;; ++c) {
+      if (*c == ' ' || *c == '\0') { if (cur_opt.rfind("-D", 0) == 0) extra.push_back(cur_opt); cur_opt.clear(); if (!*c) break; }
+      else cur_opt += *c;
+    }
+  }
+  std::vector<const char*> key_vec = {"--gpu-architecture=sm_100a", fmad ? "--fmad=true" : "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
+  for (const std::string& x : extra) key_vec.push_back(x.c_str());
+  const char* const* key_opts = key_vec.data();
+  const int n_key_opts = (int)key_vec.size();
   std::string dir, path;
   if (cubin) {
     dir = cache_dir();
     if (!dir.empty()) {
-      path = dir + "/" + cache_key(program, key_opts, 7) + ".cubin";
+      path = dir + "/" + cache_key(program, key_opts, n_key_opts) + ".cubin";
       if (cache_load(path, cubin)) {
         if (trace) fprintf(stderr, "[sde trace] nvrtc: cache hit %s\n", path.c_str());
         if (log) log->clear();
@@ -316,7 +328,7 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
   nvrtcResult r = nvrtcCreateProgram(&prog, program.c_str(), "sde_user.cu", sde_embedded_count,
                                      sde_embedded_sources, sde_embedded_names);
   if (r != NVRTC_SUCCESS) return fail(SDE_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
-  r = nvrtcCompileProgram(prog, 7, key_opts);
+  r = nvrtcCompileProgram(prog, n_key_opts, key_opts);
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
   std::string lg(ls, '\0');

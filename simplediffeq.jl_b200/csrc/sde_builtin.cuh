@@ -11,8 +11,15 @@
 
 namespace sde {
 
+// staged kernels: four CTAs per SM is what their shared-memory footprint allows (StageCfg) -- hold ptxas to the
+// 128 registers that go with it, except where the stage vectors alone need more (FP64 Verner methods, large states)
+template <class Method, class T, int N, bool STAGED>
+struct FixedMinBlocks {
+  static constexpr bool kHeavy = (Method::kNB > 7 && sizeof(T) == 8) || N > 4;
+  static constexpr int value = (STAGED && !kHeavy) ? 4 : 1;
+};
 template <class Sys, class T, class Method, int SAVE, bool Q2, bool STAGED>
-__global__ void __launch_bounds__(SDE_BLOCK) fixed_kernel(const __grid_constant__ KArgs<T> a) {
+__global__ void __launch_bounds__(SDE_BLOCK, FixedMinBlocks<Method, T, Sys::N, STAGED>::value) fixed_kernel(const __grid_constant__ KArgs<T> a) {
   fixed_body<Sys, T, Method, SAVE, Q2, STAGED>(a);
 }
 

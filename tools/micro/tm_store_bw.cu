@@ -68,6 +68,51 @@ __global__ void tm_store(double* out, long long n_rows, int row_elems, int sub, 
   if (acc == 12345.678) *sink = acc;
 }
 
+
+// The real row: ROW = 3003 doubles = 24 024 B, so rows start at every multiple of 8 bytes mod 128.
+//  pattern 0 "slots": what the staged writer does -- runs of `sub` doubles from the row start; the aligned 16-byte
+//             middle as one bulk copy, the odd element in front / behind by a scalar store of the lane.
+//  pattern 1 "lines": the same bytes, but a lane only ever writes WHOLE 128-byte lines of global memory (the
+//             partial line at the end of a run waits for the next run); row ends by scalar stores.
+__global__ void tm_real(double* out, long long n_rows, int row_elems, int sub, int pace, int pattern, double* sink) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int cap = sub + 18;                                      // doubles of staging per lane
+  double* my = reinterpret_cast<double*>(smem) + (long long)threadIdx.x * cap;
+  double acc = (double)threadIdx.x;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
+    const long long e_row = row * row_elems;                     // element offset of the row
+    double* g = out + e_row;
+    long long done = 0;                                          // elements of the row already written
+    for (int s0 = 0; s0 < row_elems; s0 += sub) {
+      const int cnt = min(sub, row_elems - s0);
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      const int it = pace * (cnt / 3);
+      for (int i = 0; i < it; ++i) acc = fma(acc, 1.0000001, 0.5);
+      my[0] = acc;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const long long avail = s0 + cnt;                          // elements produced so far
+      long long lo = done, hi = avail;                           // candidate range [lo, hi)
+      if (pattern == 1 && avail < row_elems) {
+        // keep the tail that does not fill a 128-byte line (16 doubles) of global memory
+        const long long abs_hi = e_row + hi;
+        hi -= (abs_hi & 15);
+      }
+      if (hi > lo) {
+        // scalar stores up to the first 16-byte boundary (pattern 0) / 128-byte boundary is implied by `done` (pattern 1)
+        long long a0 = lo;
+        if ((e_row + a0) & 1) { g[a0] = acc; ++a0; }
+        long long a1 = hi;
+        if ((e_row + a1) & 1) { --a1; g[a1] = acc; }
+        if (a1 > a0) bulk(g + a0, my + ((e_row + a0) & 1), (unsigned)(a1 - a0) * 8u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        done = hi;
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (acc == 12345.678) *sink = acc;
+}
+
 // the round-1 pattern for comparison: a warp writes one chunk of each of its 32 rows with plain coalesced stores
 __global__ void coop(double* out, long long n_rows, int row_elems, int chunk) {
   const int lane = threadIdx.x & 31;
@@ -124,6 +169,34 @@ int main(int argc, char** argv) {
            gb / best * 1e3, e == cudaSuccess ? "" : cudaGetErrorString(e));
     fflush(stdout);
   };
+
+
+  // (0) the real row length (3003 doubles): slot-aligned runs (what the kernel does) against whole-line flushes
+  if (argc > 1) {
+    const int row3 = 3003;
+    const double gb3 = n_rows * row3 * 8.0 / 1e9;
+    for (int pace : {0, 20, 37})
+      for (int cps : {2, 3, 4})
+        for (int sub : {36, 48, 60, 96})
+          for (int pattern : {0, 1}) {
+            const size_t sh = (size_t)128 * (sub + 18) * 8;
+            if ((sh + 1024) * cps > 227 * 1024) continue;
+            cudaFuncSetAttribute(tm_real, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+            float best = 1e9;
+            for (int r = 0; r < 2; ++r) {
+              cudaEventRecord(a);
+              tm_real<<<sms * cps, 128, sh>>>(d, n_rows, row3, sub, pace, pattern, sink);
+              cudaEventRecord(b);
+              cudaEventSynchronize(b);
+              float ms; cudaEventElapsedTime(&ms, a, b);
+              if (ms < best) best = ms;
+            }
+            printf("real-row %s cps=%d sub=%4d B pace=%2d : %8.3f ms %6.0f GB/s %s\n", pattern ? "lines" : "slots", cps, sub * 8,
+                   pace, best, gb3 / best * 1e3, cudaGetErrorString(cudaGetLastError()));
+            fflush(stdout);
+          }
+    return 0;
+  }
 
   // (1) plain bulk copies: rows in flight x copy size, unpaced and paced
   for (int pace : {0, 9, 37})
