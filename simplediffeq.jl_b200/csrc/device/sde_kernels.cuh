@@ -16,6 +16,10 @@
 #include "sde_common.cuh"
 #include "sde_methods_gen.cuh"
 
+#ifndef SDE_STEP_UNROLL
+#define SDE_STEP_UNROLL 1
+#endif
+
 namespace sde {
 
 // ------------------------------------------------------------------------------------------
@@ -186,12 +190,20 @@ struct SeriesWriter {
   unsigned lane;
   u64 gbase0;    // byte address of the warp's first row               (warp uniform)
   int nrows;     // trajectories of the warp that exist                (warp uniform)
-  // direct stores: a running element offset instead of re-deriving (slot * N + c) * ld_out + traj at every put()
-  i64 off;       // element offset of the next slot (warp-uniform: lives in the uniform datapath)
+  // direct stores
+  T* q0;         // component 0 of the next slot
+  i64 cs, ss;    // element strides between components / between slots (warp uniform)
 
   __device__ __forceinline__ SeriesWriter(const KArgs<T>& a_, i64 traj_, bool valid_)
       : a(a_), traj(traj_), valid(valid_), slot(0), wstage(nullptr), buf(nullptr), wpos(0), wb(0), lines(0),
-        gline(nullptr), lane(0), gbase0(0), nrows(0), off(0) {
+        gline(nullptr), lane(0), gbase0(0), nrows(0), q0(nullptr), cs(0), ss(0) {
+    if (!STAGED) {
+      if (a.layout == kLayoutTrajMajor) {      // out_u[(traj * n_out + slot) * N + c]
+        q0 = a.out_u + traj * a.n_out * N; cs = 1; ss = N;
+      } else {                                 // out_u[(slot * N + c) * ld_out + traj]
+        q0 = a.out_u + traj; cs = a.ld_out; ss = N * a.ld_out;
+      }
+    }
     if (STAGED) {
       lane = threadIdx.x & 31u;
       // the warp's index as a value ptxas knows to be warp-uniform
@@ -287,22 +299,13 @@ struct SeriesWriter {
       ++slot;
       if (wb >= Cfg::K0 * Cfg::kLineE) flush_lines();
     } else {
-      // strides straight from the kernel parameters (constant-bank operands): no per-thread stride registers
-      if (a.layout == kLayoutTrajMajor) {                      // out_u[(traj * n_out + slot) * N + c]
-        if (valid) {
-          T* q = a.out_u + (traj * a.n_out * N + off);
+      // one running pointer; the layout only enters through the two strides (no branch, no re-derived
+      // (slot * N + c) * ld_out + traj per save point: 9 instead of 19 instructions for the three Lorenz stores)
+      if (valid) {
 #pragma unroll
-          for (int c = 0; c < N; ++c) q[c] = v[c];
-        }
-        off += N;
-      } else {                                                 // out_u[(slot * N + c) * ld_out + traj]
-        if (valid) {
-          T* q = a.out_u + (off + traj);
-#pragma unroll
-          for (int c = 0; c < N; ++c) q[c * a.ld_out] = v[c];
-        }
-        off += N * a.ld_out;
+        for (int c = 0; c < N; ++c) q0[c * cs] = v[c];
       }
+      q0 += ss;
       ++slot;
     }
   }
@@ -367,41 +370,35 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   //   staged kernels run few warps per SM next to a large shared-memory carve-out, and a global-memory round trip
   //   per save point was their largest stall (profiles/r2_ncu_trajmajor_staged.txt).  There the warp fetches the
   //   weights of a step ONE STEP AHEAD -- each lane two 16-byte pieces, coalesced, into registers at the top of the
-  //   previous step (with ~100 GB of output streaming through L2 the table does not stay cached: a fetch issued
-  //   only before the step's own stages still showed up as 16 % of the stall samples) -- parks them in its
-  //   shared-memory ring at the top of the step, and the save loop reads them back as warp-wide broadcasts
-  //   (LDS.128): no global load, no register rotation in the loop.  Save points beyond the ring's capacity
-  //   (more than kRingSaves in one step) read their weights from global memory.
+  //   previous step -- parks them in its shared-memory ring at the top of the step, and the save loop reads them
+  //   back as warp-wide broadcasts (LDS.128): no global load, no register rotation in the loop.  (cp.async straight
+  //   into the ring needs no registers but can only start once the previous save loop has released the ring, i.e.
+  //   with the stages as its only cover: measured 6 % slower, profiles/r2_tm_variants_line_aligned.txt.)  Save
+  //   points beyond the ring's capacity (more than kRingSaves in one step) read their weights from global memory.
   constexpr int kNB = Method::kNB;
   constexpr int kNBP = plan_stride<T>(kNB);
   typedef StageCfg<T, N> SCfg;
-  typedef typename Vec16<T>::type V16;
   constexpr int kVA = 16 / (int)sizeof(T);
   constexpr int kRingSaves = SCfg::kRingElems / kNBP;                     // save points per ring load
   constexpr int kUnitsPerLane = SCfg::kRingBytes / 16 / 32;               // 16-byte pieces per lane and ring load
   constexpr bool kRing = kStaged && SAVE == kSaveAt;
   static_assert(!kRing || kRingSaves >= 1, "weights of one save point must fit the ring");
-  constexpr int kWR = kRing ? kUnitsPerLane : 1;
-  V16 wreg[kWR];
+  static_assert(kUnitsPerLane == 2, "two 16-byte pieces per lane");
+  typedef typename Vec16<T>::type V16;
   const unsigned lane = threadIdx.x & 31u;
+  V16 wreg0 = {}, wreg1 = {};     // (two named registers, not an array: NVRTC put a predicated V16[2] into local memory)
   // fetch(first, n): this lane's share of the weights of save points [first, first + n) into registers
   auto fetch = [&](i64 first, int n) {
     const int units = n * (kNBP / kVA);
-    const V16* gsrc = reinterpret_cast<const V16*>(a.plan_b + first * kNBP);
-#pragma unroll
-    for (int q = 0; q < kWR; ++q) {
-      const int idx = (int)lane + 32 * q;
-      if (idx < units) wreg[q] = gsrc[idx];
-    }
+    const char* gsrc = reinterpret_cast<const char*>(a.plan_b + first * kNBP) + 16u * lane;
+    if ((int)lane < units) wreg0 = load16<T>(gsrc);
+    if ((int)lane + 32 < units) wreg1 = load16<T>(gsrc + 512);
   };
   auto stash = [&](int n) {
     const int units = n * (kNBP / kVA);
-    V16* rdst = reinterpret_cast<V16*>(w.ring());
-#pragma unroll
-    for (int q = 0; q < kWR; ++q) {
-      const int idx = (int)lane + 32 * q;
-      if (idx < units) rdst[idx] = wreg[q];
-    }
+    char* rdst = reinterpret_cast<char*>(w.ring()) + 16u * lane;
+    if ((int)lane < units) store16<T>(rdst, wreg0);
+    if ((int)lane + 32 < units) store16<T>(rdst + 512, wreg1);
   };
   const T dt = a.dt;
   // The number of save points of a step is known BEFORE its stages (a warp-uniform load whose latency hides
@@ -416,14 +413,19 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     }
     if (a.n_steps >= 2) cnt_next = a.plan_cnt[2];
   }
+  // SDE_STEP_UNROLL = 2: two steps per trip, so that ptxas renames registers across the pair instead of copying
+  // u -> uprev and (FSAL) k7 -> k1 at the end of every step (12 moves per Lorenz step).  Measured (B200,
+  // profiles/r2_saveat_step_unroll_ab.txt): -9 % on the SoA kernel at dt = 0.1 (108 registers: a CTA per SM less),
+  // +1.5 % at dt = 0.01 -- off.
+  constexpr int kStepUnroll = SDE_STEP_UNROLL;
+#pragma unroll(kStepUnroll)
   for (i64 s = 1; s <= a.n_steps; ++s) {
     int cnt = 0;
     if (SAVE == kSaveAt) {
       if (kRing) {
         cnt = cnt_cur;
-        const int nring = cnt < kRingSaves ? cnt : kRingSaves;
         __syncwarp();                             // every lane is done with the previous contents of the ring
-        stash(nring);
+        stash(cnt < kRingSaves ? cnt : kRingSaves);
         __syncwarp();
         cnt_cur = __shfl_sync(FULL, cnt_next, 0);
         fetch(cur + cnt, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);

@@ -42,22 +42,28 @@ def emul():
     os.makedirs(OUT_DIR, exist_ok=True)
     lib = os.path.join(OUT_DIR, "libkernel_emul_%s.so" % h.hexdigest()[:16])
     if not os.path.exists(lib):
-        for old in os.listdir(OUT_DIR):
-            if old.startswith("libkernel_emul_"):
-                os.remove(os.path.join(OUT_DIR, old))
-        # verbatim copies of the device headers, except the one `extern __shared__` declaration (see the harness)
-        inc = os.path.join(OUT_DIR, "device_headers")
-        os.makedirs(inc, exist_ok=True)
-        replaced = 0
-        for f in files[1:]:
-            text = open(f).read()
-            decl = "extern __shared__ __align__(16) unsigned char sde_dyn_smem[];"
-            replaced += text.count(decl)
-            with open(os.path.join(inc, os.path.basename(f)), "w") as fh:
-                fh.write(text.replace(decl, "EMUL_DYN_SMEM"))
-        assert replaced == 1
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-                               "-I", inc, "-I", os.path.join(ROOT, "simplediffeq.jl_b200", "csrc"), SRC, "-o", lib])
+        import fcntl
+        with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:      # pytest-xdist: one worker builds, the others wait
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if not os.path.exists(lib):
+                for old in os.listdir(OUT_DIR):
+                    if old.startswith("libkernel_emul_"):
+                        os.remove(os.path.join(OUT_DIR, old))
+                # verbatim copies of the device headers, except the one `extern __shared__` declaration (see the harness)
+                inc = os.path.join(OUT_DIR, "device_headers")
+                os.makedirs(inc, exist_ok=True)
+                replaced = 0
+                for f in files[1:]:
+                    text = open(f).read()
+                    decl = "extern __shared__ __align__(16) unsigned char sde_dyn_smem[];"
+                    replaced += text.count(decl)
+                    with open(os.path.join(inc, os.path.basename(f)), "w") as fh:
+                        fh.write(text.replace(decl, "EMUL_DYN_SMEM"))
+                assert replaced == 1
+                tmp = lib + ".tmp.%d" % os.getpid()
+                subprocess.check_call(["g++", "-O1", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                                       "-I", inc, "-I", os.path.join(ROOT, "simplediffeq.jl_b200", "csrc"), SRC, "-o", tmp])
+                os.rename(tmp, lib)
     L = ctypes.CDLL(lib)
     vp, ll, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double
     L.emul_solve.restype = ctypes.c_int
