@@ -462,9 +462,10 @@ def warp32(emul):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("algname", ["GPUSimpleTsit5", "GPUSimpleRK4", "GPUSimpleVern7"])
 def test_staged_trajectory_major_writer_with_32_lanes(warp32, sde, oracle, algname, dtype):
-    """The shared-memory staged series writer (every warp buffers S slots of its 32 trajectories, half-warps flush
-    contiguous runs) as 32 cooperating host threads: ragged last warp (n = 70), partial last flush, every-step and
-    saveat outputs -- bit-identical to the oracle."""
+    """The shared-memory staged series writer (every lane stages its row's byte stream, the warp writes whole 128-byte
+    lines and slides the rest to the front; weights of a step through the warp's ring) as 32 cooperating host threads:
+    ragged last warp (n = 70), first line / row end by the owner lane, every-step and saveat outputs -- bit-identical
+    to the oracle."""
     n = 70
     u0, p = C.random_problem("lorenz", n, dtype, seed=21)
     tspan, dt = (0.0, 1.0), 0.02
@@ -480,6 +481,25 @@ def test_staged_trajectory_major_writer_with_32_lanes(warp32, sde, oracle, algna
         gs = _run(warp32, "lorenz", algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=0, saveat=saveat,
                   n_out=len(saveat), compat=16)
         assert C.bits_equal(gs["u"], os_.u)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("system,algname", [("vanderpol", "GPUSimpleTsit5"), ("scalargrowth", "GPUSimpleTsit5"),
+                                            ("lorenz", "GPUSimpleVern9"), ("nonautonomous", "GPUSimpleVern7")])
+def test_staged_writer_row_alignments_and_ring_overflow_with_32_lanes(warp32, sde, oracle, system, algname, dtype):
+    """State sizes 1, 2 and 3 (rows start at every multiple of the element size mod 128 bytes), 401 save points at 25
+    per step -- more than the weight ring holds, so the tail of every step reads its weights from global memory --
+    and enough slots for many line flushes per row: bit-identical to the oracle."""
+    n = 45
+    u0, p = C.random_problem(system, n, dtype, seed=29)
+    tspan, dt = (0.0, 1.0), 0.0625
+    tg = _grid(sde, tspan, dt, dtype)
+    saveat = sde.jl_range(dtype(0.0), dtype(0.0025), dtype(1.0), dtype)
+    o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg, saveat=saveat,
+                     n_threads=4)
+    g = _run(warp32, system, algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=0, saveat=saveat, n_out=len(saveat),
+             compat=16)
+    assert C.bits_equal(g["u"], o.u), "max ulp diff %d" % C.max_ulp_diff(g["u"], o.u)
 
 
 @pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8),
