@@ -13,6 +13,16 @@ u0s, ps = np.ascontiguousarray(u0.T), np.ascontiguousarray(p.T)
 sa = np.linspace(0, 1, 41)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, saveat=sa, save_mode=1, layout=0)   # staged writer
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleVern7(), u0s, ps, (0.0, 1.0), dt=0.05, save_mode=2, layout=0)             # staged, every step
+# staged writer: many whole-line flushes per row, more save points per step than the weight ring holds, rows of every
+# alignment (state sizes 1 and 2, Float32), ragged last warp
+dense = S.jl_range(0.0, 0.0025, 1.0)
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.0625, saveat=dense, save_mode=1, layout=0)
+for name in ("vanderpol", "scalargrowth"):
+    for dt_ in (np.float64, np.float32):
+        a0, b0 = C.random_problem(name, 333, dt_, 2)
+        S.solve_arrays(getattr(S.systems, name), S.GPUSimpleTsit5(), np.ascontiguousarray(a0.T), np.ascontiguousarray(b0.T), (0.0, 1.0),
+                       dt=0.0625, saveat=S.jl_range(dt_(0.0), dt_(0.0025), dt_(1.0), dt_), save_mode=1, layout=0)
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleRK4(), u0s, ps, (0.0, 1.0), dt=0.002, save_mode=2, layout=0)               # 501 slots per row
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7)           # work queue
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleAVern9(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-9, reltol=1e-9, saveat=sa, save_mode=1, layout=1)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7, save_mode=2, out_capacity=64)
