@@ -607,16 +607,28 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         if (kStrict) {
           // the reference's arithmetic, operation for operation (gpuatsit5.jl:276-292):
           // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol) ; ODE_DEFAULT_NORM
+          // (divisions: strict_div() = the fast path of CUDA's own IEEE division without its branch, sde_common.cuh;
+          //  a group whose range tests all pass is done, otherwise the group is recomputed with plain divisions)
+          T den[N], sc[N];
+#pragma unroll
+          for (int c = 0; c < N; ++c) den[c] = a.abstol + max_abs_nan2(uprev[c], u[c]) * a.reltol;
+          bool ok = true;
+#pragma unroll
+          for (int c = 0; c < N; ++c) sc[c] = strict_div(e[c], den[c], ok);
+          if (!ok) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) sc[c] = e[c] / den[c];
+          }
           if (N == 1) {
-            EEst = sde_abs(e[0] / (a.abstol + max_abs_nan2(uprev[0], u[0]) * a.reltol));
+            EEst = sde_abs(sc[0]);
           } else {
             T ssum = T(0);
 #pragma unroll
-            for (int c = 0; c < N; ++c) {
-              const T sc = e[c] / (a.abstol + max_abs_nan2(uprev[c], u[c]) * a.reltol);
-              ssum = (c == 0) ? sc * sc : ssum + sc * sc;
-            }
-            EEst = sde_sqrt(ssum / T(N));
+            for (int c = 0; c < N; ++c) ssum = (c == 0) ? sc[c] * sc[c] : ssum + sc[c] * sc[c];
+            ok = true;
+            T mean = strict_div(ssum, T(N), ok);
+            if (!ok) mean = ssum / T(N);
+            EEst = sde_sqrt(mean);
           }
           accept = !(EEst > T(1));
           // q11 = EEst^beta1: log half once (kept for qold^beta2 below), exp half per exponent; anything but a
@@ -628,11 +640,19 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           // reject: dt /= min(inv(qmin), q11 / gamma)     (EEst > 1, so q11 / gamma > 1: the lower clamp is a no-op and
           //         the NaN rule of Base.min is never exercised)
           // both as straight-line code: the lanes of a warp part only at the late branch below
-          T q = accept ? q11 / qoldpow : q11;
+          ok = true;
+          T q = accept ? strict_div(q11, qoldpow, ok) : q11;
           if (EEst == T(0)) q = inv_qmax;
-          q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
+          q = max_fast(inv_qmax, min_fast(inv_qmin, strict_div(q, gamma, ok)));
+          T dtnew = strict_div(dt, q, ok);
+          if (!ok) {
+            q = accept ? q11 / qoldpow : q11;
+            if (EEst == T(0)) q = inv_qmax;
+            q = max_fast(inv_qmax, min_fast(inv_qmin, q / gamma));
+            dtnew = dt / q;
+          }
           if (accept) dtold = dt;
-          dt = dt / q;
+          dt = dtnew;
         } else {
           // same formulas in the log2 domain (see sde_common.cuh); lqold = beta2 * log2(qold)
           constexpr int LB = CtrlLog2<T>::kBase;
