@@ -19,6 +19,11 @@
 #ifndef SDE_STEP_UNROLL
 #define SDE_STEP_UNROLL 1
 #endif
+// Weight ring of the staged kernels (fixed_body): 0 = register fetch one step ahead (built-in kernels), 1 = cp.async into
+// the ring at the end of the previous step (no registers; what the launcher selects for NVRTC systems)
+#ifndef SDE_RING_CPASYNC
+#define SDE_RING_CPASYNC 0
+#endif
 
 namespace sde {
 
@@ -371,9 +376,11 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   //   per save point was their largest stall (profiles/r2_ncu_trajmajor_staged.txt).  There the warp fetches the
   //   weights of a step ONE STEP AHEAD -- each lane two 16-byte pieces, coalesced, into registers at the top of the
   //   previous step -- parks them in its shared-memory ring at the top of the step, and the save loop reads them
-  //   back as warp-wide broadcasts (LDS.128): no global load, no register rotation in the loop.  (cp.async straight
-  //   into the ring needs no registers but can only start once the previous save loop has released the ring, i.e.
-  //   with the stages as its only cover: measured 6 % slower, profiles/r2_tm_variants_line_aligned.txt.)  Save
+  //   back as warp-wide broadcasts (LDS.128): no global load, no register rotation in the loop.  cp.async straight
+  //   into the ring (SDE_RING_CPASYNC) needs no registers but can only start once the previous save loop has released
+  //   the ring, i.e. with the stages as its only cover: 6 % slower in the built-in kernels, but 6.5 % FASTER under NVRTC,
+  //   whose code spills exactly those registers at the 128-register cap (profiles/r2_tm_variants_line_aligned.txt) --
+  //   so the launcher compiles user systems with it.  Save
   //   points beyond the ring's capacity (more than kRingSaves in one step) read their weights from global memory.
   constexpr int kNB = Method::kNB;
   constexpr int kNBP = plan_stride<T>(kNB);
@@ -400,6 +407,16 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
     if ((int)lane < units) store16<T>(rdst, wreg0);
     if ((int)lane + 32 < units) store16<T>(rdst + 512, wreg1);
   };
+  // the same pieces by cp.async straight into the ring (SDE_RING_CPASYNC)
+  auto ring_fetch = [&](i64 first, int n) {
+    const int units = n * (kNBP / kVA);
+    const char* gsrc = reinterpret_cast<const char*>(a.plan_b + first * kNBP) + 16u * lane;
+    char* rdst = reinterpret_cast<char*>(w.ring()) + 16u * lane;
+    if ((int)lane < units) async_copy16(rdst, gsrc);
+    if ((int)lane + 32 < units) async_copy16(rdst + 512, gsrc + 512);
+    async_copy_commit();
+  };
+  constexpr bool kAsyncRing = SDE_RING_CPASYNC != 0;
   const T dt = a.dt;
   // The number of save points of a step is known BEFORE its stages (a warp-uniform load whose latency hides
   // behind the stages; comparing a prefetched "step of the next save point" after every save point left an L1
@@ -409,7 +426,8 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   if (kRing) {
     if (a.n_steps >= 1) {
       cnt_cur = __shfl_sync(FULL, a.plan_cnt[1], 0);     // the same value, but one ptxas knows to be warp-uniform
-      fetch(cur, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
+      if (kAsyncRing) ring_fetch(cur, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
+      else fetch(cur, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
     }
     if (a.n_steps >= 2) cnt_next = a.plan_cnt[2];
   }
@@ -422,7 +440,9 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
   for (i64 s = 1; s <= a.n_steps; ++s) {
     int cnt = 0;
     if (SAVE == kSaveAt) {
-      if (kRing) {
+      if (kRing && kAsyncRing) {
+        cnt = cnt_cur;                            // (its weights were requested at the end of the previous step)
+      } else if (kRing) {
         cnt = cnt_cur;
         __syncwarp();                             // every lane is done with the previous contents of the ring
         stash(cnt < kRingSaves ? cnt : kRingSaves);
@@ -446,6 +466,10 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
         m.template dense_prepare<Q2>(uprev, p, t, dt);   // extra stages do not depend on theta: once per step; time base = advanced t (Q3)
         int k = 0;
         if (kRing) {
+          if (kAsyncRing) {
+            async_copy_wait_all();                // this lane's pieces of the ring have landed ...
+            __syncwarp();                         // ... and so have everybody else's
+          }
           const int nring = cnt < kRingSaves ? cnt : kRingSaves;
           const T* rb = w.ring();
           for (; k < nring; ++k) {
@@ -464,6 +488,12 @@ __device__ __forceinline__ void fixed_body(const KArgs<T>& a) {
           w.put(o);
         }
         cur += cnt;
+      }
+      if (kRing && kAsyncRing) {      // the ring is free: start on the weights of the next step
+        cnt_cur = __shfl_sync(FULL, cnt_next, 0);
+        __syncwarp();
+        ring_fetch(cur, cnt_cur < kRingSaves ? cnt_cur : kRingSaves);
+        cnt_next = (s + 2 <= a.n_steps) ? a.plan_cnt[s + 2] : 0;
       }
     }
   }

@@ -307,7 +307,8 @@ int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::str
       else cur_opt += *c;
     }
   }
-  std::vector<const char*> key_vec = {"--gpu-architecture=sm_100a", fmad ? "--fmad=true" : "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k};
+  std::vector<const char*> key_vec = {"--gpu-architecture=sm_100a", fmad ? "--fmad=true" : "--fmad=false", "--std=c++17", "-lineinfo", "-default-device", tune_k, tune32_k,
+                                     "-DSDE_RING_CPASYNC=1"};     // weight ring of the staged kernels: see sde_kernels.cuh
   for (const std::string& x : extra) key_vec.push_back(x.c_str());
   const char* const* key_opts = key_vec.data();
   const int n_key_opts = (int)key_vec.size();

@@ -30,8 +30,7 @@ FIXED = ["GPUSimpleTsit5", "GPUSimpleRK4", "GPUSimpleVern7", "GPUSimpleVern9", "
 ADAPT = ["GPUSimpleATsit5", "GPUSimpleAVern7", "GPUSimpleAVern9"]
 
 
-@pytest.fixture(scope="session")
-def emul():
+def _build_emul(defines=()):
     """g++ -O1 -mfma -ffp-contract=off (only the explicit fma() calls fuse, like -fmad=false on the device; -O1 compiles
     a third faster than -O2 and IEEE results do not depend on the level);
     rebuilt when the harness or any device header changes."""
@@ -40,14 +39,18 @@ def emul():
     for f in files:
         h.update(open(f, "rb").read())
     os.makedirs(OUT_DIR, exist_ok=True)
-    lib = os.path.join(OUT_DIR, "libkernel_emul_%s.so" % h.hexdigest()[:16])
+    for d in defines:
+        h.update(d.encode())
+    tag = "".join(c for c in "_".join(defines) if c.isalnum() or c == "_")
+    prefix = "libkernel_emul%s_" % (("_" + tag) if tag else "")
+    lib = os.path.join(OUT_DIR, prefix + "%s.so" % h.hexdigest()[:16])
     if not os.path.exists(lib):
         import fcntl
         with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:      # pytest-xdist: one worker builds, the others wait
             fcntl.flock(lock, fcntl.LOCK_EX)
             if not os.path.exists(lib):
                 for old in os.listdir(OUT_DIR):
-                    if old.startswith("libkernel_emul_"):
+                    if old.startswith(prefix) and old[len(prefix):len(prefix) + 16].isalnum() and len(old) == len(prefix) + 19:
                         os.remove(os.path.join(OUT_DIR, old))
                 # verbatim copies of the device headers, except the one `extern __shared__` declaration (see the harness)
                 inc = os.path.join(OUT_DIR, "device_headers")
@@ -61,7 +64,7 @@ def emul():
                         fh.write(text.replace(decl, "EMUL_DYN_SMEM"))
                 assert replaced == 1
                 tmp = lib + ".tmp.%d" % os.getpid()
-                subprocess.check_call(["g++", "-O1", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                subprocess.check_call(["g++", "-O1", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"] + list(defines) + [
                                        "-I", inc, "-I", os.path.join(ROOT, "simplediffeq.jl_b200", "csrc"), SRC, "-o", tmp])
                 os.rename(tmp, lib)
     L = ctypes.CDLL(lib)
@@ -69,6 +72,18 @@ def emul():
     L.emul_solve.restype = ctypes.c_int
     L.emul_solve.argtypes = [ctypes.c_int] * 6 + [ll, vp, vp, d, d, d, d, d, ll, vp, vp, ll, ll, ll, vp, vp, vp, vp, vp]
     return L
+
+
+@pytest.fixture(scope="session")
+def emul():
+    return _build_emul()
+
+
+@pytest.fixture(scope="session")
+def emul_async_ring():
+    """The same harness with the staged kernels' weight ring filled by cp.async (SDE_RING_CPASYNC = 1): what the launcher
+    compiles for NVRTC systems."""
+    return _build_emul(("-DSDE_RING_CPASYNC=1",))
 
 
 def _ptr(a):
@@ -500,6 +515,29 @@ def test_staged_writer_row_alignments_and_ring_overflow_with_32_lanes(warp32, sd
     g = _run(warp32, system, algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=0, saveat=saveat, n_out=len(saveat),
              compat=16)
     assert C.bits_equal(g["u"], o.u), "max ulp diff %d" % C.max_ulp_diff(g["u"], o.u)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("system,algname", [("lorenz", "GPUSimpleTsit5"), ("scalargrowth", "GPUSimpleVern7")])
+def test_staged_writer_with_the_cp_async_weight_ring(emul_async_ring, sde, oracle, system, algname, dtype):
+    """The weight ring variant that NVRTC systems are compiled with (cp.async at the end of the previous step instead of
+    a register fetch one step ahead): same cases as above, 32 lanes, bit-identical to the oracle."""
+    L = emul_async_ring
+    L.emul_set_lanes.argtypes = [ctypes.c_int]
+    assert L.emul_set_lanes(32) == 0
+    try:
+        n = 45
+        u0, p = C.random_problem(system, n, dtype, seed=31)
+        tspan, dt = (0.0, 1.0), 0.0625
+        tg = _grid(sde, tspan, dt, dtype)
+        for saveat in (sde.jl_range(dtype(0.0), dtype(0.0025), dtype(1.0), dtype), np.linspace(0.0, 1.0, 38).astype(dtype)):
+            o = oracle.solve(system, C.ALG_NAMES[algname], u0, p, tspan[0], tspan[1], dt, dtype=dtype, tgrid=tg,
+                             saveat=saveat, n_threads=4)
+            g = _run(L, system, algname, u0, p, tspan, dt, tgrid=tg, save=1, layout=0, saveat=saveat, n_out=len(saveat),
+                     compat=16)
+            assert C.bits_equal(g["u"], o.u), "max ulp diff %d" % C.max_ulp_diff(g["u"], o.u)
+    finally:
+        assert L.emul_set_lanes(1) == 0
 
 
 @pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8),
