@@ -13,7 +13,7 @@
 //            each one is a rendezvous: deposit the operand, barrier, read the others', barrier.  __shared__ arrays
 //            are shared by the block, atomicAdd is a real atomic.  This runs the warp-aggregated work queue
 //            (ballot / popc prefix / leader atomic / shuffle), the warp-vote exit and the shared-memory STAGED
-//            trajectory-major writer (half-warp flushes between __syncwarp()s) as 32 cooperating lanes.
+//            trajectory-major writer (whole-line flushes and the per-warp weight ring between __syncwarp()s) as 32 cooperating lanes.
 // Blocks run one after the other.  The only arithmetic that differs
 // from the device is the seed of sde_rcp_fast: MUFU.RCP64H there, the IEEE quotient 1.0 / x here (the float seed
 // that SDE_HOST_EMULATION selects in sde_common.cuh overflows for |x| > 3.4e38, which blown-up trajectories reach;
