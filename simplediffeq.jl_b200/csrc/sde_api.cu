@@ -93,6 +93,11 @@ int tune_stage_elems() {
   const char* e = getenv("SDE_TUNE_STAGE_ELEMS");
   return e ? atoi(e) : 0;
 }
+// SDE_TUNE_MIN_BLOCKS=<n> (development, NVRTC systems only): second __launch_bounds__ argument of the fixed-step kernels
+int tune_min_blocks() {
+  const char* e = getenv("SDE_TUNE_MIN_BLOCKS");
+  return e ? atoi(e) : 0;
+}
 size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
   int elems = es == 8 ? 48 : 96;
   if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
@@ -226,7 +231,7 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
     snprintf(buf, sizeof buf,
              "extern \"C\" __global__ void __launch_bounds__(%d, %d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
              "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
-             kBlock, (staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1, method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
+             kBlock, tune_min_blocks() > 0 ? tune_min_blocks() : ((staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1), method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
   }
   s += buf;
   return s;

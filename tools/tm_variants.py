@@ -52,5 +52,8 @@ for i, v in enumerate(variants):
     stage = [w for w in words if w.startswith("stage=")]
     os.environ.pop("SDE_TUNE_STAGE_ELEMS", None)
     if stage: os.environ["SDE_TUNE_STAGE_ELEMS"] = stage[0][6:]
+    mb = [w for w in words if w.startswith("minblocks=")]
+    os.environ.pop("SDE_TUNE_MIN_BLOCKS", None)
+    if mb: os.environ["SDE_TUNE_MIN_BLOCKS"] = mb[0][10:]
     os.environ["SDE_TUNE_DEFINES"] = " ".join(w for w in words if w.startswith("-D"))
     timed(S.CudaRHS(SRC + "\n// variant %d\n" % i, 3, 3), "nvrtc [%s]" % v)
