@@ -463,25 +463,35 @@ def solve_arrays(system, alg, u0_soa, p_soa, tspan, *, dt, abstol=1e-6, reltol=1
 
 def solve_device(system, alg, d_u0, d_p, tspan, *, dt, abstol=1e-6, reltol=1e-3, saveat=None,
                  save_mode=_lib.SAVE_ENDPOINT, layout=_lib.LAYOUT_TRAJ_MAJOR, compat=0, maxiters=0,
-                 out=None, stats=True, stream=None, sync=True):
+                 out=None, stats=True, stream=None, sync=True, out_capacity=0):
     """Device-resident entry: d_u0 [n_state, n] and d_p [n_param, n] are torch CUDA tensors (SoA);
-    returns torch tensors on the same device.  torch only provides memory and the stream."""
+    returns torch tensors on the same device.  torch only provides memory and the stream.
+    Adaptive algorithms with save_mode = SAVE_EVERYSTEP need `out_capacity` slots per trajectory (rows that are too
+    short come back with retcode OUTPUT_FULL and the needed count in naccept, like the C ABI reports them); the time of
+    every slot is returned as `t_series`."""
     import torch
     assert d_u0.is_cuda and d_u0.is_contiguous()
     dtype = np.dtype(np.float64) if d_u0.dtype == torch.float64 else np.dtype(np.float32)
     N, n = d_u0.shape
     keep = []
+    every = alg.adaptive and save_mode == _lib.SAVE_EVERYSTEP
+    if every and out_capacity < 1:
+        raise ValueError("adaptive save_everystep needs out_capacity >= 1 slots per trajectory")
     o = make_options(alg, dtype, n, tspan, dt, abstol, reltol, saveat, save_mode, layout, compat,
-                     maxiters, keep)
+                     maxiters, keep, out_capacity=int(out_capacity) if every else 0)
+    slots = 1
+    if save_mode != _lib.SAVE_ENDPOINT:
+        slots = int(o.n_save) if save_mode == _lib.SAVE_SAVEAT else (int(out_capacity) if every else int(o.n_steps) + 1)
     if out is None:
         if save_mode == _lib.SAVE_ENDPOINT:
             shape = (N, n)
         else:
-            slots = int(o.n_save) if save_mode == _lib.SAVE_SAVEAT else int(o.n_steps) + 1
             shape = (n, slots, N) if layout == _lib.LAYOUT_TRAJ_MAJOR else (slots, N, n)
         out = torch.empty(shape, dtype=d_u0.dtype, device=d_u0.device)
-    t_final = nacc = nrej = ret = None
-    if alg.adaptive:
+    t_final = nacc = nrej = ret = t_series = None
+    if every:       # the C ABI's out_t holds the time of every slot in this mode
+        t_series = torch.empty((n, slots) if layout == _lib.LAYOUT_TRAJ_MAJOR else (slots, n), dtype=d_u0.dtype, device=d_u0.device)
+    elif alg.adaptive:
         t_final = torch.empty(n, dtype=d_u0.dtype, device=d_u0.device)
     if stats and alg.adaptive:
         nacc = torch.zeros(n, dtype=torch.int32, device=d_u0.device)
@@ -493,8 +503,8 @@ def solve_device(system, alg, d_u0, d_p, tspan, *, dt, abstol=1e-6, reltol=1e-3,
     with torch.cuda.device(d_u0.device):
         rc = _lib.lib().sde_solve_device(system._handle, ctypes.byref(o), d_u0.data_ptr(),
                                          ptr(d_p) if d_p is not None and d_p.numel() else None, n,
-                                         out.data_ptr(), n, ptr(t_final), ptr(nacc), ptr(nrej), ptr(ret),
+                                         out.data_ptr(), n, ptr(t_series if every else t_final), ptr(nacc), ptr(nrej), ptr(ret),
                                          st, 0 if sync else 1)
     _lib.check(rc)
-    return dict(u=out, t_final=t_final, naccept=nacc, nreject=nrej, retcode=ret, n_steps=int(o.n_steps),
+    return dict(u=out, t_final=t_final, t_series=t_series, naccept=nacc, nreject=nrej, retcode=ret, n_steps=int(o.n_steps),
                 options=o, keep=keep)

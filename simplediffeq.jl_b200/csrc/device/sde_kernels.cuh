@@ -564,11 +564,92 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
   int cur = 0, nacc = 0, nrej = 0;
   i64 traj = -1;
   bool active = false, drained = false;
+  // ---- every accepted step kept (the reference's default, save_everystep = true), trajectory-major rows ----------
+  // A lane appending its N values per accepted step to its own row writes 32 different rows per instruction, N * sizeof(T)
+  // bytes each (measured, config-1 sweep at 2^20: 5.1x the endpoint-only solve; the NaN fill of the unused capacity went
+  // the same way).  Here every lane keeps the open end of its row in a two-line ring of shared memory that is congruent
+  // with global memory mod 128 bytes; at the top of every iteration the warp writes out the lines that became complete
+  // (four rows per pass, eight lanes per line: LDS.128 -> STG.128), and rows that ended get their last partial line from
+  // their owner and their unused capacity (NaN, like the reference's undef) from the whole warp.  Lanes are NOT in
+  // lockstep here (work queue), hence ballots instead of the fixed-step writer's warp-uniform counters.
+  // Needs N * sizeof(T) <= 64: a row grows by at most two slots between two services (u0 and the first accepted step of a
+  // refilled lane), which must fit next to a pending partial line.  Times go straight to out_t (8 bytes per step).
+  constexpr bool kRowStage = (SAVE == kSaveEveryStep) && (N * (int)sizeof(T) <= kRowStageMaxSlotBytes);
+  const bool rowstage = kRowStage && a.layout == kLayoutTrajMajor && blockDim.x >= 32;
+  constexpr int kLineE = 128 / (int)sizeof(T);
+  constexpr int kRingE = 2 * kLineE;
+  T* rs_ring = reinterpret_cast<T*>(sde_dyn_smem + (size_t)threadIdx.x * kRowStageStrideB);
+  int rs_wpos = 0;          // next element of the row stream (element 0 = start of the line that holds the row's start)
+  int rs_lines = 0;         // lines of the row stream already in global memory
+  i64 rs_end = 0;           // end of the row in the same coordinates
+  char* rs_gline = nullptr; // global address of row-stream element 0
+  bool rs_open = false, rs_fin = false;
+  auto row_append = [&](const T* v) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) rs_ring[(rs_wpos + c) & (kRingE - 1)] = v[c];
+    rs_wpos += N;
+  };
+  auto row_phi = [&]() {    // offset of the row's start in its first line, in elements (recomputed: once or twice per row)
+    return (int)(((u64)a.out_u + (u64)(traj * a.n_out * N) * sizeof(T)) & (u64)127) / (int)sizeof(T);
+  };
+  auto row_service = [&]() {
+    // (1) lines that became complete since the last service (at most one per lane)
+    const bool ready = rs_open && (rs_wpos / kLineE > rs_lines);
+    unsigned mask = __ballot_sync(FULL, ready);
+    const unsigned char* wbase = sde_dyn_smem + (size_t)(threadIdx.x & ~31u) * kRowStageStrideB;
+    while (mask) {
+      unsigned mm = mask;
+      const int r0 = __ffs(mm) - 1; mm &= mm - 1u;
+      const int r1 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
+      const int r2 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
+      const int r3 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
+      const unsigned j = lane >> 3, piece = lane & 7u;
+      const int row = j == 0 ? r0 : (j == 1 ? r1 : (j == 2 ? r2 : r3));
+      const int from = row < 0 ? 0 : row;
+      const int L = __shfl_sync(FULL, rs_lines, from);
+      const u64 gl = __shfl_sync(FULL, (u64)rs_gline, from);
+      if (row >= 0 && L > 0)      // (line 0 is shared with the previous row: its owner writes its part below)
+        copy16<T>(reinterpret_cast<char*>(gl) + (size_t)L * 128 + piece * 16u,
+                  wbase + (size_t)from * kRowStageStrideB + (size_t)(L & 1) * 128 + piece * 16u);
+      mask = mm;
+    }
+    if (ready) {
+      if (rs_lines == 0) {
+        T* g = reinterpret_cast<T*>(rs_gline);
+        for (int e = row_phi(); e < kLineE; ++e) g[e] = rs_ring[e];
+      }
+      ++rs_lines;
+    }
+    // (2) rows that ended: the pending partial line by its owner, the unused capacity by the warp
+    unsigned fmask = __ballot_sync(FULL, rs_fin);
+    if (fmask) {
+      if (rs_fin) {
+        T* g = reinterpret_cast<T*>(rs_gline);
+        for (int e = (rs_lines == 0) ? row_phi() : rs_lines * kLineE; e < rs_wpos; ++e) g[e] = rs_ring[e & (kRingE - 1)];
+      }
+      const T nan = sde_nan(T(0));
+      while (fmask) {
+        const int r = __ffs(fmask) - 1;
+        fmask &= fmask - 1u;
+        T* g = reinterpret_cast<T*>(__shfl_sync(FULL, (u64)rs_gline, r));
+        const i64 from = (i64)__shfl_sync(FULL, rs_wpos, r), to = __shfl_sync(FULL, rs_end, r);
+        for (i64 e = from + lane; e < to; e += 32) g[e] = nan;
+        const i64 tr = __shfl_sync(FULL, traj, r);
+        const int na = __shfl_sync(FULL, nacc, r);
+        if (a.out_t) {
+          T* gt = a.out_t + tr * a.n_out;
+          for (i64 sl = (i64)na + 1 + lane; sl < a.n_out; sl += 32) gt[sl] = nan;
+        }
+      }
+      if (rs_fin) { rs_fin = false; rs_open = false; }
+    }
+  };
   // attempts are counted as nacc + nrej (int32, like the naccept / nreject outputs); 0 = the
   // reference's "no maxiters" = the int32 range
   const int attempt_limit = (a.max_attempts > 0 && a.max_attempts < (i64)0x7fffffff) ? (int)a.max_attempts : 0x7fffffff;
 
   for (;;) {
+    if (rowstage) row_service();
     // ---- work queue: idle lanes fetch the next trajectory (one atomic per warp per refill).
     // Fast path while every lane is busy: one vote.
     if (__any_sync(FULL, !active)) {
@@ -597,11 +678,22 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
               }
             }
             if (SAVE == kSaveEveryStep) {   // us = [u0], ts = [t0]   (gpuatsit5.jl:220-224)
-              put_series<T, N>(a, traj, 0, u);
+              if (rowstage) {
+                const u64 mine = (u64)a.out_u + (u64)(traj * a.n_out * N) * sizeof(T);
+                rs_gline = reinterpret_cast<char*>(mine & ~(u64)127);
+                rs_wpos = (int)(mine & (u64)127) / (int)sizeof(T);
+                rs_end = (i64)rs_wpos + a.n_out * N;
+                rs_lines = 0;
+                rs_open = true;
+                row_append(u);
+              } else {
+                put_series<T, N>(a, traj, 0, u);
+              }
               put_series_time<T>(a, traj, 0, t);
             }
             active = true;
             if (!(t < tf)) {   // `while t < tspan[2]` never entered
+              if (rowstage) rs_fin = true;      // (the row still gets its slot 0 and its NaN capacity)
               if (SAVE == kSaveEndpoint) put_endpoint<T, N>(a, traj, u);
               if (SAVE != kSaveEveryStep && a.out_t) a.out_t[traj] = t;
               if (a.naccept) a.naccept[traj] = 0;
@@ -615,7 +707,10 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         }
       }
       if (__all_sync(FULL, !active)) {
-        if (__all_sync(FULL, drained)) break;   // warp-vote exit: nothing left anywhere
+        if (__all_sync(FULL, drained)) {        // warp-vote exit: nothing left anywhere
+          if (rowstage) row_service();          // (a row that ended inside this refill)
+          break;
+        }
         continue;
       }
     }
@@ -757,7 +852,8 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
           }
           if (SAVE == kSaveEveryStep) {   // push!(us, u); push!(ts, t)   (gpuatsit5.jl:301-303)
             if ((i64)nacc < a.n_out) {
-              put_series<T, N>(a, traj, nacc, u);
+              if (rowstage) row_append(u);
+              else put_series<T, N>(a, traj, nacc, u);
               put_series_time<T>(a, traj, nacc, t);
             }
           }
@@ -794,12 +890,16 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
         }
         if (SAVE == kSaveEveryStep) {
           if (ret == kRetDefault && (i64)nacc >= a.n_out) ret = kRetOutputFull;
-          T nanv[N];
+          if (rowstage) {
+            rs_fin = true;              // last partial line + unused capacity: row_service() at the top of the next iteration
+          } else {
+            T nanv[N];
 #pragma unroll
-          for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
-          for (i64 s = (i64)nacc + 1; s < a.n_out; ++s) {   // unused capacity
-            put_series<T, N>(a, traj, s, nanv);
-            put_series_time<T>(a, traj, s, nanv[0]);
+            for (int c = 0; c < N; ++c) nanv[c] = sde_nan(T(0));
+            for (i64 s = (i64)nacc + 1; s < a.n_out; ++s) {   // unused capacity
+              put_series<T, N>(a, traj, s, nanv);
+              put_series_time<T>(a, traj, s, nanv[0]);
+            }
           }
         } else if (a.out_t) {
           a.out_t[traj] = t;

@@ -82,6 +82,12 @@ bool want_strict(const sde_options_t* o) {
 bool want_staged(const sde_options_t* o) {
   return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
 }
+// adaptive save_everystep in the trajectory-major layout: rows through a two-line shared-memory ring per lane
+// (sde::adaptive_body; the kernel derives the same condition from its template arguments and KArgs::layout)
+bool want_row_stage(const sde_options_t* o, int n_state) {
+  return is_adaptive(o->alg) && o->save_mode == SDE_SAVE_EVERYSTEP && o->layout == SDE_LAYOUT_TRAJ_MAJOR &&
+         n_state * (o->dtype == SDE_F64 ? 8 : 4) <= sde::kRowStageMaxSlotBytes;
+}
 int64_t out_slots(const sde_options_t* o) {
   if (o->save_mode == SDE_SAVE_SAVEAT) return o->n_save;
   if (o->save_mode == SDE_SAVE_EVERYSTEP) return is_adaptive(o->alg) ? o->out_capacity : o->n_steps + 1;
@@ -593,10 +599,18 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   SDE_CUDA(cudaGetDevice(&dev));
   unsigned grid;
   const int64_t full = (o->n_traj + kBlock - 1) / kBlock;
+  size_t smem = 0;
+  if (want_staged(o)) {
+    smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
+  } else if (want_row_stage(o, sys->n_state)) {
+    smem = (size_t)kBlock * sde::kRowStageStrideB;       // adaptive every-step rows (adaptive_body)
+  }
+  if (smem > 48 * 1024)
+    SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (adaptive) {
     SDE_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
     SDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+    SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem));
     if (per_sm < 1) per_sm = 1;
     grid = (unsigned)std::min<int64_t>(full, (int64_t)sms * per_sm);   // persistent CTAs
   } else {
@@ -606,12 +620,6 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
     if (d_nacc) SDE_CUDA(cudaMemsetAsync(d_nacc, 0, 4 * (size_t)o->n_traj, st));
     if (d_nrej) SDE_CUDA(cudaMemsetAsync(d_nrej, 0, 4 * (size_t)o->n_traj, st));
     if (d_ret) SDE_CUDA(cudaMemsetAsync(d_ret, 0, 4 * (size_t)o->n_traj, st));
-  }
-  size_t smem = 0;
-  if (want_staged(o)) {
-    smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
-    if (smem > 48 * 1024)
-      SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   void* params[] = {&a};
   SDE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), params, smem, st));

@@ -561,6 +561,42 @@ def test_work_queue_with_32_lanes_equals_one_lane(warp32, emul, oracle, system, 
     assert np.all(g32["retcode"] == 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("system,algname,tspan,tol", [("lorenz", "GPUSimpleATsit5", (0.0, 10.0), 1e-8),
+                                                      ("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6),
+                                                      ("scalargrowth", "GPUSimpleAVern7", (0.0, 3.0), 1e-9),
+                                                      ("lorenz", "GPUSimpleAVern9", (0.0, 2.0), 1e-10)])
+def test_adaptive_everystep_rows_through_the_shared_memory_ring(warp32, emul, system, algname, tspan, tol, dtype):
+    """Adaptive save_everystep (the reference's default) in the trajectory-major layout: with full warps every lane keeps the
+    open end of its row in a two-line shared-memory ring, complete lines are written by the warp (ballot, four rows per
+    pass), a finished row gets its last partial line from its owner and its unused capacity (NaN) from the warp.  Unequal
+    step counts (shuffled sweep), refills, n not a multiple of 32, rows of every alignment (state sizes 1, 2, 3; both
+    dtypes), a capacity that is too small for some rows (OUTPUT_FULL): states, times, counts and return codes equal the
+    one-lane run -- which stores directly -- bit for bit, NaN fill included."""
+    n = 77
+    if system == "lorenz":
+        u0, p = C.lorenz_sweep(n, dtype)
+        p = p[(np.arange(n) * 2654435761) % n]
+    elif system == "vanderpol":
+        u0, p = C.vdp_sweep(n, dtype, shuffled=True)
+    else:
+        u0, p = C.random_problem(system, n, dtype, seed=5)
+    dt0 = float(np.float32(0.1))
+    tol = max(tol, 1e-5) if dtype is np.float32 else tol
+    assert emul.emul_set_lanes(1) == 0
+    ref = _run(emul, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=4096)
+    caps = [int(ref["naccept"].max()) + 1, int(np.median(ref["naccept"]))]       # exact fit; too small for half the rows
+    for cap in caps:
+        g1 = _run(emul, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=cap)
+        assert emul.emul_set_lanes(32) == 0
+        g32 = _run(warp32, system, algname, u0, p, tspan, dt0, abstol=tol, reltol=tol, save=2, layout=0, n_out=cap)
+        assert emul.emul_set_lanes(1) == 0
+        for k in ("u", "t", "naccept", "nreject", "retcode"):
+            assert C.bits_equal(g32[k], g1[k]), (k, cap)
+        assert np.any(g1["retcode"] == 3) == (cap == caps[1])
+    assert emul.emul_set_lanes(32) == 0        # (the warp32 fixture resets to one lane on exit)
+
+
 @pytest.mark.parametrize("system,algname,tspan,tol", [("vanderpol", "GPUSimpleATsit5", (0.0, 20.0), 1e-6),
                                                       ("lorenz", "GPUSimpleAVern9", (0.0, 10.0), 1e-12)])
 def test_literal_controller_with_32_lanes_is_the_oracle_bit_for_bit(warp32, oracle, system, algname, tspan, tol):

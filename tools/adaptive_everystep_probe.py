@@ -1,0 +1,39 @@
+"""Development aid: adaptive save_everystep = true (the reference's default) on the config-1 sweep at 2^20 trajectories,
+both layouts, against the endpoint-only solve."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import simplediffeq_b200 as S
+dev = torch.device("cuda:0")
+n = 1 << 20
+dt0 = float(np.float32(0.1))
+u0 = torch.zeros(3, n, dtype=torch.float64, device=dev); u0[0] = 1
+p = torch.empty(3, n, dtype=torch.float64, device=dev); p[0] = 10; p[2] = 8.0 / 3.0
+p[1] = 21.0 * torch.arange(n, dtype=torch.float64, device=dev) / (n - 1)
+
+
+def timed(fn, reps=3):
+    out = fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+for shuffled in (False, True):
+    pp = p
+    if shuffled:
+        perm = (torch.arange(n, dtype=torch.int64, device=dev) * 2654435761) % n
+        pp = p[:, perm].contiguous()
+    ms0, r = timed(lambda: S.solve_device(S.systems.lorenz, S.GPUSimpleATsit5(), u0, pp, (0.0, 10.0), dt=dt0, abstol=1e-8, reltol=1e-8, sync=False))
+    acc = int(r["naccept"].sum().item()); cap = int(r["naccept"].max().item()) + 1
+    print("%s endpoint only: %.2f ms  %.3g accepted steps/s (capacity needed %d slots)" % ("shuffled" if shuffled else "sorted", ms0, acc / ms0 * 1e3, cap), flush=True)
+    for layout, nm in ((1, "SoA"), (0, "trajectory-major")):
+        ms, r = timed(lambda: S.solve_device(S.systems.lorenz, S.GPUSimpleATsit5(), u0, pp, (0.0, 10.0), dt=dt0, abstol=1e-8, reltol=1e-8,
+                                             save_mode=2, layout=layout, out_capacity=cap, sync=False))
+        written = (acc + n) * 32          # states + times actually stored
+        print("   every step, %-16s: %.2f ms (%.2fx endpoint)  %.3g accepted steps/s  %.0f GB/s of stored states+times; buffer %.1f GB"
+              % (nm, ms, ms / ms0, acc / ms * 1e3, written / ms / 1e6, n * cap * 32 / 1e9), flush=True)
+    del r
+    torch.cuda.empty_cache()
