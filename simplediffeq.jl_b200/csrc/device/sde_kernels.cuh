@@ -593,32 +593,37 @@ __device__ __forceinline__ void adaptive_body(const KArgs<T>& a) {
     return (int)(((u64)a.out_u + (u64)(traj * a.n_out * N) * sizeof(T)) & (u64)127) / (int)sizeof(T);
   };
   auto row_service = [&]() {
-    // (1) lines that became complete since the last service (at most one per lane)
+    // (1) lines that became complete since the last service (at most one per lane).  Every ready lane publishes
+    // where its line lies (shared-memory offset) and where it goes (global address) under its rank among the ready
+    // lanes; then eight lanes move one line, four lines per pass.
     const bool ready = rs_open && (rs_wpos / kLineE > rs_lines);
-    unsigned mask = __ballot_sync(FULL, ready);
-    const unsigned char* wbase = sde_dyn_smem + (size_t)(threadIdx.x & ~31u) * kRowStageStrideB;
-    while (mask) {
-      unsigned mm = mask;
-      const int r0 = __ffs(mm) - 1; mm &= mm - 1u;
-      const int r1 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
-      const int r2 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
-      const int r3 = mm ? __ffs(mm) - 1 : -1; mm = mm ? (mm & (mm - 1u)) : 0u;
-      const unsigned j = lane >> 3, piece = lane & 7u;
-      const int row = j == 0 ? r0 : (j == 1 ? r1 : (j == 2 ? r2 : r3));
-      const int from = row < 0 ? 0 : row;
-      const int L = __shfl_sync(FULL, rs_lines, from);
-      const u64 gl = __shfl_sync(FULL, (u64)rs_gline, from);
-      if (row >= 0 && L > 0)      // (line 0 is shared with the previous row: its owner writes its part below)
-        copy16<T>(reinterpret_cast<char*>(gl) + (size_t)L * 128 + piece * 16u,
-                  wbase + (size_t)from * kRowStageStrideB + (size_t)(L & 1) * 128 + piece * 16u);
-      mask = mm;
-    }
-    if (ready) {
-      if (rs_lines == 0) {
-        T* g = reinterpret_cast<T*>(rs_gline);
-        for (int e = row_phi(); e < kLineE; ++e) g[e] = rs_ring[e];
+    const unsigned mask = __ballot_sync(FULL, ready);
+    if (mask) {
+      unsigned char* wbase = sde_dyn_smem + (size_t)(threadIdx.x & ~31u) * kRowStageStrideB;
+      RowLineMeta* meta = reinterpret_cast<RowLineMeta*>(sde_dyn_smem + (size_t)blockDim.x * kRowStageStrideB) + (threadIdx.x & ~31u);
+      if (ready) {
+        RowLineMeta mt;
+        // (line 0 is shared with the previous row: its owner writes its part below, the warp skips it)
+        mt.dst = rs_lines > 0 ? (u64)(rs_gline + (size_t)rs_lines * 128) : 0;
+        mt.src = (unsigned)(lane * kRowStageStrideB + (rs_lines & 1) * 128);
+        mt.pad = 0;
+        meta[__popc(mask & ((1u << lane) - 1u))] = mt;
       }
-      ++rs_lines;
+      __syncwarp();
+      const int nready = __popc(mask);
+      const unsigned piece = (lane & 7u) * 16u;
+      for (int k = (int)(lane >> 3); k < nready; k += 4) {
+        const RowLineMeta mt = meta[k];
+        if (mt.dst) copy16<T>(reinterpret_cast<char*>(mt.dst) + piece, wbase + mt.src + piece);
+      }
+      __syncwarp();
+      if (ready) {
+        if (rs_lines == 0) {
+          T* g = reinterpret_cast<T*>(rs_gline);
+          for (int e = row_phi(); e < kLineE; ++e) g[e] = rs_ring[e];
+        }
+        ++rs_lines;
+      }
     }
     // (2) rows that ended: the pending partial line by its owner, the unused capacity by the warp
     unsigned fmask = __ballot_sync(FULL, rs_fin);

@@ -603,7 +603,7 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   if (want_staged(o)) {
     smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, !sys->builtin);
   } else if (want_row_stage(o, sys->n_state)) {
-    smem = (size_t)kBlock * sde::kRowStageStrideB;       // adaptive every-step rows (adaptive_body)
+    smem = (size_t)kBlock * sde::kRowStageBytesPerThread;       // adaptive every-step rows (adaptive_body): rings + line table
   }
   if (smem > 48 * 1024)
     SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -12,14 +12,23 @@ p = torch.empty(3, n, dtype=torch.float64, device=dev); p[0] = 10; p[2] = 8.0 / 
 p[1] = 21.0 * torch.arange(n, dtype=torch.float64, device=dev) / (n - 1)
 
 
-def timed(fn, reps=3):
-    out = fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): out = fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps, out
+def timed(fn, reps=4):
+    """best of `reps` individually timed launches after two untimed ones (the first calls grow torch's caching allocator by
+    tens of GB: a cudaMalloc inside a timed region reads as a 100 ms kernel)"""
+    out = fn(); out = fn(); torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best, out
 
+
+# bring the SM clock up before the first timed kernel
+import time
+t_end = time.time() + 1.0
+while time.time() < t_end:
+    S.solve_device(S.systems.lorenz, S.GPUSimpleTsit5(), u0, p, (0.0, 10.0), dt=1e-2, stats=False, sync=True)
 
 for shuffled in (False, True):
     pp = p
