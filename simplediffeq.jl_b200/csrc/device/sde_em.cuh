@@ -22,6 +22,7 @@
 //   tprev = fma(i, dt, t0) (:68), sqdt = sqrt(dt) (:69)
 #pragma once
 #include "sde_common.cuh"
+#include "sde_series.cuh"
 
 namespace sde {
 
@@ -130,36 +131,43 @@ struct NoiseStream {
   }
 };
 
-template <class T, int N>
-__device__ __forceinline__ void em_put(const EMArgs<T>& a, i64 traj, i64 slot, const T* v) {
-  if (a.layout == kLayoutTrajMajor) {
-    T* o = a.out_u + (traj * (a.n_steps + 1) + slot) * N;
-#pragma unroll
-    for (int c = 0; c < N; ++c) o[c] = v[c];
-  } else {
-#pragma unroll
-    for (int c = 0; c < N; ++c) a.out_u[(slot * N + c) * a.ld_out + traj] = v[c];
-  }
-}
-
 // SAVE: kSaveEndpoint | kSaveEveryStep (the reference's behaviour)
-template <class Sys, class T, int SAVE, int NOISE>
-__device__ __forceinline__ void em_body(const EMArgs<T>& a) {
+// STAGED: every state of a trajectory goes through the fixed-step kernels' series writer (sde_series.cuh): trajectory-major
+// rows staged in shared memory and written in whole 128-byte lines (GBM, 4 Mi paths x 255 steps, FP64: 13.3 -> see
+// profiles/r2_em_everystep.txt); the lanes of a warp stay together then (lanes beyond the ensemble integrate a copy of the
+// last trajectory and never write)
+template <class Sys, class T, int SAVE, int NOISE, bool STAGED>
+__device__ __forceinline__ void em_body_impl(const EMArgs<T>& a) {
   constexpr int N = Sys::N, NP = Sys::NP, M = Sys::M;
   constexpr bool kDiag = Sys::kDiagonal;
+  constexpr bool kStaged = STAGED && SAVE == kSaveEveryStep;
   CtrlTab tab = nullptr;
   if (NOISE == kNoisePhilox && sizeof(T) == 8) tab = em_load_table();
   const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (traj >= a.n_traj) return;
+  const bool valid = traj < a.n_traj;
+  if (!kStaged) {
+    if (!valid) return;
+  } else {
+    if (traj - (i64)(threadIdx.x & 31u) >= a.n_traj) return;
+  }
+  const i64 src = valid ? traj : a.n_traj - 1;
   T u[N], p[NP > 0 ? NP : 1];
 #pragma unroll
-  for (int c = 0; c < N; ++c) u[c] = a.u0[(i64)c * a.ld_in + traj];
+  for (int c = 0; c < N; ++c) u[c] = a.u0[(i64)c * a.ld_in + src];
 #pragma unroll
-  for (int c = 0; c < NP; ++c) p[c] = a.p[(i64)c * a.ld_in + traj];
+  for (int c = 0; c < NP; ++c) p[c] = a.p[(i64)c * a.ld_in + src];
   const T dt = a.dt;
   const T sqdt = sde_sqrt(dt);
-  NoiseStream<T, NOISE> ns(a, traj, tab);
-  if (SAVE == kSaveEveryStep) em_put<T, N>(a, traj, 0, u);
+  NoiseStream<T, NOISE> ns(a, src, tab);
+  // the writer only looks at the output description of its argument block
+  KArgs<T> ka;
+  ka.n_traj = a.n_traj;
+  ka.layout = a.layout;
+  ka.out_u = a.out_u;
+  ka.ld_out = a.ld_out;
+  ka.n_out = a.n_steps + 1;
+  SeriesWriter<T, N, kStaged> w(ka, traj, valid);
+  if (SAVE == kSaveEveryStep) w.put(u);
   for (i64 s = 0; s < a.n_steps; ++s) {
     const T tprev = fma((T)s, dt, a.t0);
     T f[N], g[kDiag ? N : N * M], z[M];
@@ -187,12 +195,21 @@ __device__ __forceinline__ void em_body(const EMArgs<T>& a) {
 #pragma unroll
       for (int i = 0; i < N; ++i) u[i] = un[i];
     }
-    if (SAVE == kSaveEveryStep) em_put<T, N>(a, traj, s + 1, u);
+    if (SAVE == kSaveEveryStep) w.put(u);
   }
+  if (SAVE == kSaveEveryStep) w.finish();
   if (SAVE == kSaveEndpoint) {
 #pragma unroll
     for (int c = 0; c < N; ++c) a.out_u[(i64)c * a.ld_out + traj] = u[c];
   }
+}
+
+// staged rows when the launch asked for the trajectory-major layout (the launcher then provides the writer's dynamic
+// shared memory: sde_em_api.cu) -- a run-time property of the launch, so both forms live in the every-step kernels
+template <class Sys, class T, int SAVE, int NOISE>
+__device__ __forceinline__ void em_body(const EMArgs<T>& a) {
+  if (SAVE == kSaveEveryStep && a.layout == kLayoutTrajMajor && blockDim.x >= 32) em_body_impl<Sys, T, SAVE, NOISE, true>(a);
+  else em_body_impl<Sys, T, SAVE, NOISE, false>(a);
 }
 
 // writes the normals a kNoisePhilox solve with the same (seed, traj_offset) consumes:

@@ -59,6 +59,30 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// dynamic shared memory of the staged writer: must mirror sde::StageCfg
+// Tuning knob (NVRTC systems only, development): SDE_TUNE_STAGE_ELEMS=<elements staged per lane>
+int tune_stage_elems() {
+  const char* e = getenv("SDE_TUNE_STAGE_ELEMS");
+  return e ? atoi(e) : 0;
+}
+// SDE_TUNE_MIN_BLOCKS=<n> (development, NVRTC systems only): second __launch_bounds__ argument of the fixed-step kernels
+int tune_min_blocks() {
+  const char* e = getenv("SDE_TUNE_MIN_BLOCKS");
+  return e ? atoi(e) : 0;
+}
+size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
+  int elems = es == 8 ? 48 : 96;
+  if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
+  // StageCfg::kCapB: the configured capacity, at least one line + line offset + one slot, an odd number of 16-byte units
+  const int sz = (int)es;
+  const int need = (128 - sz) + 128 + (n_state * sz - sz);
+  const int want = elems * sz + 16;
+  const int raw = (std::max(want, need) + 15) / 16 * 16;
+  const int cap = ((raw / 16) % 2 == 0) ? raw + 16 : raw;
+  // per warp: 32 lane regions + the 1 KB ring of dense-output weights (StageCfg::kBytesPerWarp)
+  return (size_t)(block / 32) * ((size_t)32 * cap + 1024);
+}
+
 }  // namespace sde_host
 using namespace sde_host;
 
@@ -93,30 +117,6 @@ int64_t out_slots(const sde_options_t* o) {
   if (o->save_mode == SDE_SAVE_EVERYSTEP) return is_adaptive(o->alg) ? o->out_capacity : o->n_steps + 1;
   return 1;
 }
-// dynamic shared memory of the staged writer: must mirror sde::StageCfg
-// Tuning knob (NVRTC systems only, development): SDE_TUNE_STAGE_ELEMS=<elements staged per lane>
-int tune_stage_elems() {
-  const char* e = getenv("SDE_TUNE_STAGE_ELEMS");
-  return e ? atoi(e) : 0;
-}
-// SDE_TUNE_MIN_BLOCKS=<n> (development, NVRTC systems only): second __launch_bounds__ argument of the fixed-step kernels
-int tune_min_blocks() {
-  const char* e = getenv("SDE_TUNE_MIN_BLOCKS");
-  return e ? atoi(e) : 0;
-}
-size_t staged_smem_bytes(int n_state, size_t es, int block, bool user) {
-  int elems = es == 8 ? 48 : 96;
-  if (user && tune_stage_elems() > 0) elems = tune_stage_elems();
-  // StageCfg::kCapB: the configured capacity, at least one line + line offset + one slot, an odd number of 16-byte units
-  const int sz = (int)es;
-  const int need = (128 - sz) + 128 + (n_state * sz - sz);
-  const int want = elems * sz + 16;
-  const int raw = (std::max(want, need) + 15) / 16 * 16;
-  const int cap = ((raw / 16) % 2 == 0) ? raw + 16 : raw;
-  // per warp: 32 lane regions + the 1 KB ring of dense-output weights (StageCfg::kBytesPerWarp)
-  return (size_t)(block / 32) * ((size_t)32 * cap + 1024);
-}
-
 struct Compiled {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;

@@ -196,8 +196,16 @@ int em_launch_t(sde_em_system_s* sys, const sde_em_options_t* o, const void* fn,
   a.noise_ld = noise_ld;
   const int64_t grid = (o->n_traj + kBlock - 1) / kBlock;
   if (grid > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
+  // every state kept, trajectory-major rows: the kernel takes the staged series writer (sde_em.cuh: em_body), which
+  // needs its dynamic shared memory
+  size_t smem = 0;
+  if (o->save_mode == SDE_SAVE_EVERYSTEP && o->layout == SDE_LAYOUT_TRAJ_MAJOR) {
+    smem = staged_smem_bytes(sys->n_state, sizeof(T), kBlock, false);
+    if (smem > 48 * 1024)
+      SDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   void* params[] = {&a};
-  SDE_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kBlock), params, 0, st));
+  SDE_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kBlock), params, smem, st));
   g_launches.fetch_add(1);
   return SDE_OK;
 }

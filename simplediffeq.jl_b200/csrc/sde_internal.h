@@ -27,6 +27,10 @@ inline size_t esize(int dtype) { return dtype == SDE_F64 ? 8 : 4; }
 int device_pool(int dev, cudaMemPool_t* out);
 size_t pool_keep_bytes();
 
+// dynamic shared memory of the staged series writer (sde::StageCfg::kBytesPerWarp per warp); `user`: NVRTC system
+// (honours the development knob SDE_TUNE_STAGE_ELEMS)
+size_t staged_smem_bytes(int n_state, size_t es, int block, bool user);
+
 // NVRTC: compile `program` (device headers are embedded in the library) to a cubin for sm_100a
 int nvrtc_compile(const std::string& program, std::vector<char>* cubin, std::string* log, bool fmad = false);
 
