@@ -499,6 +499,32 @@ def test_staged_trajectory_major_writer_with_32_lanes(warp32, sde, oracle, algna
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("system", list(EM_SYS))
+def test_em_every_state_through_the_staged_writer_with_32_lanes(warp32, oracle, system, dtype):
+    """SimpleEM keeping every state in the trajectory-major layout goes through the fixed-step kernels' staged series
+    writer (sde_em.cuh: em_body -> em_body_impl<STAGED>; sde_series.cuh) when the CTA has whole warps: 32 cooperating
+    host threads, a ragged last warp (lanes beyond the ensemble integrate a copy of the last path and never write), rows
+    of 1- and 2-component states in both dtypes, many whole-line flushes per row -- bit-identical to the oracle and to
+    the SoA layout's direct stores."""
+    L = _em_lib(warp32)
+    n, steps, dt = 45, 150, 1 / 256
+    rng = np.random.default_rng(8)
+    u0, p, M = EM_PROBLEMS[system]
+    u0s = (np.array(u0)[:, None] * (1 + 0.2 * rng.uniform(-1, 1, (len(u0), n)))).astype(dtype)
+    ps = (np.array(p)[:, None] * (1 + 0.2 * rng.uniform(-1, 1, (len(p), n)))).astype(dtype)
+    z = rng.standard_normal((steps, M, n)).astype(dtype)
+    want = oracle.em_solve(system, u0s, ps, 0.25, dt, steps, z)                      # [n][steps+1][N]
+    tm = _em_run(L, system, u0s, ps, 0.25, dt, steps, noise=z, layout=0)
+    assert C.bits_equal(tm, want)
+    soa = _em_run(L, system, u0s, ps, 0.25, dt, steps, noise=z, layout=1)
+    assert C.bits_equal(np.ascontiguousarray(soa.transpose(2, 0, 1)), want)
+    # Philox noise: the staged path consumes the same stream as the direct one
+    a = _em_run(L, system, u0s, ps, 0.0, dt, steps, seed=5, layout=0)
+    b = _em_run(L, system, u0s, ps, 0.0, dt, steps, seed=5, layout=1)
+    assert C.bits_equal(a, np.ascontiguousarray(b.transpose(2, 0, 1)))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("system,algname", [("vanderpol", "GPUSimpleTsit5"), ("scalargrowth", "GPUSimpleTsit5"),
                                             ("lorenz", "GPUSimpleVern9"), ("nonautonomous", "GPUSimpleVern7")])
 def test_staged_writer_row_alignments_and_ring_overflow_with_32_lanes(warp32, sde, oracle, system, algname, dtype):

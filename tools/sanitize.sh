@@ -32,6 +32,10 @@ z = np.random.default_rng(0).standard_normal((16, 4, n))
 S.solve_em_arrays(S.sde_systems.gbm, np.ones((1, n)), np.tile([[0.1], [0.2]], (1, n)), 0.0, 1 / 16, 16, seed=3)
 S.solve_em_arrays(S.sde_systems.nondiag2x4, np.ones((2, n)), np.full((1, n), 1.01), 0.0, 1 / 16, 16, noise=z, layout=1)
 S.em_noise(np.float32, 5, n, 9, 3)
+# SimpleEM, every state, trajectory-major rows through the staged series writer: 1- and 2-component rows, both dtypes, ragged last warp
+S.solve_em_arrays(S.sde_systems.gbm, np.ones((1, n)), np.tile([[0.1], [0.2]], (1, n)), 0.0, 1 / 256, 200, seed=3, layout=0)
+S.solve_em_arrays(S.sde_systems.gbm, np.ones((1, n), dtype=np.float32), np.tile([[0.1], [0.2]], (1, n)).astype(np.float32), 0.0, 1 / 256, 200, seed=3, layout=0)
+S.solve_em_arrays(S.sde_systems.nondiag2x4, np.ones((2, n)), np.full((1, n), 1.01), 0.0, 1 / 16, 16, noise=z, layout=0)
 os.environ["SDE_TUNE_PIECE"] = "96"
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, saveat=sa, save_mode=1, layout=0)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7, saveat=sa, save_mode=1, layout=1)
