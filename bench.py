@@ -15,6 +15,7 @@ the configuration the headline metric is quoted on):
     2     Lorenz 10 M, GPUSimpleTsit5 fixed dt = 1e-3, 10 000 steps, FP64     (configs[1])   [default]
     2f32  the same in Float32
     2fast the same in FP64 with SDE_COMPAT_FAST_RHS (contracted right-hand side; not bit-identical to the reference)
+    2faster  ... and SDE_COMPAT_FAST_STAGES (step size folded into the stage coefficients)
     3     Van der Pol mu-sweep 2^20, GPUSimpleATsit5 tol 1e-6, sorted         (configs[2])
     3s    the same, shuffled (i -> i * 2654435761 mod n)
     4     Lorenz 1 M, GPUSimpleAVern9 tol 1e-12 (default options = literal controller)   (configs[3])
@@ -70,6 +71,12 @@ CONFIGS = {
                   desc="Lorenz rho-sweep 10M trajectories, GPUSimpleTsit5 fixed dt=0.001, FP64, endpoint only, contracted right-hand side "
                        "(SDE_COMPAT_FAST_RHS: 114 instead of 126 FP64 operations per step; NOT bit-identical to the reference, <= 1e-12 "
                        "relative on this sweep; the same 190 flops per step are counted)"),
+    "2faster": dict(baseline="configs[1] with SDE_COMPAT_FAST_RHS | SDE_COMPAT_FAST_STAGES", system="lorenz", alg="GPUSimpleTsit5", oalg="Tsit5",
+                    n=10_000_000, tspan=(0.0, 10.0), dt=1e-3, compat=24, instr=99, flop=190,
+                    desc="Lorenz rho-sweep 10M trajectories, GPUSimpleTsit5 fixed dt=0.001, FP64, endpoint only, contracted right-hand side and "
+                         "the step size folded into the stage coefficients (SDE_COMPAT_FAST_RHS | SDE_COMPAT_FAST_STAGES: 99 instead of 126 "
+                         "FP64 instructions per step; NOT bit-identical to the reference: median 5e-15 relative on this sweep, <= 1e-12 "
+                         "away from the bifurcation at rho = 13.926; the reference method's 190 flops per step are counted)"),
     "3": dict(baseline="configs[2] sorted", system="vanderpol", alg="GPUSimpleATsit5", oalg="ATsit5", n=1 << 20, tspan=(0.0, 20.0), tol=1e-6,
               desc="Van der Pol mu-sweep 2^20 trajectories (sorted), GPUSimpleATsit5 abstol=reltol=1e-6, tspan (0,20), endpoint only", instr=150),
     "3s": dict(baseline="configs[2] shuffled", system="vanderpol", alg="GPUSimpleATsit5", oalg="ATsit5", n=1 << 20, tspan=(0.0, 20.0), tol=1e-6,
@@ -92,7 +99,7 @@ CONFIGS = {
                saveat=(0.0, 0.01, 10.0), layout="soa", instr=151,
                desc="Lorenz 4M trajectories, GPUSimpleTsit5 dt=0.01 (1000 steps, ~1 save point per step) + saveat=0:0.01:10, SoA"),
 }
-EXTRA_ORDER = ["2f32", "2fast", "1", "1b", "3", "3s", "4", "4l", "5", "5f", "5tm"]
+EXTRA_ORDER = ["2f32", "2fast", "2faster", "1", "1b", "3", "3s", "4", "4l", "5", "5f", "5tm"]
 
 
 def is_adaptive(cfg):

@@ -113,7 +113,7 @@ enum {
                                       output (the reference uses k2..k9, src/verner/gpuvern9.jl:216-331) */
   SDE_COMPAT_STRICT_CONTROLLER = 2, /* adaptive: force the literal controller */
   SDE_COMPAT_LOG2_CONTROLLER = 4,   /* adaptive: force the log2-domain controller (exclusive with the above) */
-  SDE_COMPAT_FAST_RHS = 8           /* throughput beyond the reference-exact ceiling: the right-hand side f may be
+  SDE_COMPAT_FAST_RHS = 8,          /* throughput beyond the reference-exact ceiling: the right-hand side f may be
                                        contracted into fused multiply-adds (the reference never applies @muladd to
                                        f).  Built-in lorenz: 8 -> 6 FP64 instructions per evaluation, a fixed-step
                                        Tsit5 step 126 -> 114 (~ +10 % steps/s); vanderpol 5 -> 3; user CUDA-C
@@ -122,6 +122,18 @@ enum {
                                        sweep <= 1e-12 relative (median 6e-16) except within 0.01 of the homoclinic
                                        bifurcation at rho = 13.926 (max 6e-12); unbounded for chaotic trajectories,
                                        like any rounding change.  Off by default. */
+  SDE_COMPAT_FAST_STAGES = 16       /* throughput beyond the reference-exact ceiling, second step: fixed-step
+                                       GPUSimpleTsit5 keeping only the last state (save_mode ENDPOINT) folds the step
+                                       size into the stage coefficients, tmp = uprev + sum_j (dt a_ij) k_j instead
+                                       of the reference's uprev + dt (sum_j a_ij k_j): 21 N instead of 26 N + 1 FP64
+                                       instructions per step for the stage sums, any system (built-in or CUDA-C).
+                                       With SDE_COMPAT_FAST_RHS on lorenz: 126 -> 99 per step,
+                                       1.84e11 steps/s on BASELINE config 2 (+25 % over the reference-exact kernel).  Every term is then
+                                       rounded at the magnitude of the state, so the deviation from the reference
+                                       is that of one more rounding of u per stage: on BASELINE config 2's sweep
+                                       median 5e-15 relative, 99.9 % of the trajectories <= 6e-13, <= 1e-12 except
+                                       within 0.025 of rho = 13.926 (max 2.3e-11).  Other algorithms and save modes
+                                       ignore the flag.  Off by default. */
 };
 
 typedef struct sde_system_s* sde_system_t;

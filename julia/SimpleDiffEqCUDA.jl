@@ -47,6 +47,7 @@ const SDE_LAYOUT_TRAJ_MAJOR, SDE_LAYOUT_SOA = Int32(0), Int32(1)
 # states and reltol <= 1e-11; log2-domain otherwise); the flags force one of them
 const SDE_COMPAT_FIX_VERN9_INTERP, SDE_COMPAT_STRICT_CONTROLLER, SDE_COMPAT_LOG2_CONTROLLER = Int32(1), Int32(2), Int32(4)
 const SDE_COMPAT_FAST_RHS = Int32(8)    # contracted right-hand side: faster, no longer bit-identical to the CPU method
+const SDE_COMPAT_FAST_STAGES = Int32(16)    # fixed-step Tsit5, endpoint only: step size folded into the stage coefficients (same caveat)
 
 alg_id(::GPUSimpleTsit5) = Int32(0)
 alg_id(::GPUSimpleATsit5) = Int32(1)

@@ -21,6 +21,7 @@ COMPAT_FIX_VERN9_INTERP = 1
 COMPAT_STRICT_CONTROLLER = 2
 COMPAT_LOG2_CONTROLLER = 4
 COMPAT_FAST_RHS = 8
+COMPAT_FAST_STAGES = 16
 
 EXPORTS = ["sde_version", "sde_last_error", "sde_device_count", "sde_system_builtin",
            "sde_system_nvrtc", "sde_system_dims", "sde_system_free", "sde_system_prepare",

@@ -38,7 +38,7 @@ static_assert((int)sde::kRetDefault == SDE_RET_DEFAULT && (int)sde::kRetDtMin ==
 static_assert((int)sde::kCompatFixVern9Interp == SDE_COMPAT_FIX_VERN9_INTERP &&
               (int)sde::kCompatStrictController == SDE_COMPAT_STRICT_CONTROLLER &&
               (int)sde::kCompatLog2Controller == SDE_COMPAT_LOG2_CONTROLLER &&
-              (int)sde::kCompatFastRhs == SDE_COMPAT_FAST_RHS, "compat flags");
+              (int)sde::kCompatFastRhs == SDE_COMPAT_FAST_RHS && (int)sde::kCompatFastStages == SDE_COMPAT_FAST_STAGES, "compat flags");
 
 extern const char* const sde_embedded_names[];
 extern const char* const sde_embedded_sources[];
@@ -102,6 +102,10 @@ bool want_strict(const sde_options_t* o) {
   if (o->compat & SDE_COMPAT_STRICT_CONTROLLER) return true;
   if (o->compat & SDE_COMPAT_LOG2_CONTROLLER) return false;
   return o->dtype == SDE_F32 || o->reltol <= 1e-11;
+}
+// SDE_COMPAT_FAST_STAGES acts on the fixed-step Tsit5 kernel that keeps only the last state (Tsit5FastMethod)
+bool want_fast_stages(const sde_options_t* o) {
+  return (o->compat & SDE_COMPAT_FAST_STAGES) && o->alg == SDE_ALG_TSIT5 && o->save_mode == SDE_SAVE_ENDPOINT;
 }
 bool want_staged(const sde_options_t* o) {
   return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
@@ -176,7 +180,7 @@ int validate(const sde_system_s* sys, const sde_options_t* o) {
   if (o->layout != SDE_LAYOUT_TRAJ_MAJOR && o->layout != SDE_LAYOUT_SOA)
     return fail(SDE_ERR_INVALID, "unknown layout %d", o->layout);
   if (o->n_traj < 0) return fail(SDE_ERR_INVALID, "n_traj < 0");
-  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS))
+  if (o->compat & ~(SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS | SDE_COMPAT_FAST_STAGES))
     return fail(SDE_ERR_INVALID, "unknown compat flags 0x%x", (unsigned)o->compat);
   if ((o->compat & SDE_COMPAT_STRICT_CONTROLLER) && (o->compat & SDE_COMPAT_LOG2_CONTROLLER))
     return fail(SDE_ERR_INVALID, "compat flags SDE_COMPAT_STRICT_CONTROLLER and SDE_COMPAT_LOG2_CONTROLLER exclude each other");
@@ -208,7 +212,7 @@ const char* method_name(int alg) {
   }
 }
 
-std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool strict, bool staged, bool syntax_only) {
+std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, bool q2, bool strict, bool staged, bool syntax_only, bool fast_stages = false) {
   std::string s;
   s += dtype == SDE_F64 ? "typedef double real;\n" : "typedef float real;\n";
   s += "#include \"sde_kernels.cuh\"\n";
@@ -237,7 +241,9 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
     snprintf(buf, sizeof buf,
              "extern \"C\" __global__ void __launch_bounds__(%d, %d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
              "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
-             kBlock, tune_min_blocks() > 0 ? tune_min_blocks() : ((staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1), method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
+             kBlock, tune_min_blocks() > 0 ? tune_min_blocks() : ((staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1),
+             // SDE_COMPAT_FAST_STAGES, fixed-step Tsit5, endpoint only: step size folded into the stage coefficients
+             (fast_stages && alg == SDE_ALG_TSIT5 && save == SDE_SAVE_ENDPOINT) ? "sde::Tsit5FastMethod" : method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
   }
   s += buf;
   return s;
@@ -375,14 +381,15 @@ namespace {
 int get_user_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void** fn) {
   const bool q2 = want_q2(o), strict = want_strict(o), staged = want_staged(o);
   const bool fast = (o->compat & SDE_COMPAT_FAST_RHS) != 0;
+  const bool fast_stages = want_fast_stages(o);
   int dev = -1;
   if (load) SDE_CUDA(cudaGetDevice(&dev));
   char key[96];
-  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict, (int)staged, (int)fast);
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d/%d", o->alg, o->dtype, o->save_mode, (int)q2, (int)strict, (int)staged, (int)fast, (int)fast_stages);
   std::lock_guard<std::mutex> lk(sys->mu);
   Compiled& c = sys->cache[key];
   if (c.cubin.empty()) {
-    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, staged, false);
+    std::string prog = user_program(sys, o->alg, o->dtype, o->save_mode, q2, strict, staged, false, fast_stages);
     int rc = nvrtc_compile(prog, &c.cubin, nullptr, fast);
     if (rc != SDE_OK) { sys->cache.erase(key); return rc; }
   }
@@ -404,7 +411,7 @@ int get_kernel(sde_system_s* sys, const sde_options_t* o, bool load, const void*
   if (sys->builtin) {
     const sde_builtin_lookup_fn look = ((o->compat & SDE_COMPAT_FAST_RHS) && sys->lookup_fast) ? sys->lookup_fast : sys->lookup;
     sde::KernelInfo ki = look(o->alg, o->dtype, o->save_mode,
-                                     (want_q2(o) ? 1 : 0) | (want_strict(o) ? 2 : 0) | (want_staged(o) ? 4 : 0));
+                                     (want_q2(o) ? 1 : 0) | (want_strict(o) ? 2 : 0) | (want_staged(o) ? 4 : 0) | (want_fast_stages(o) ? 8 : 0));
     if (!ki.fn)
       return fail(SDE_ERR_UNSUPPORTED, "no kernel for system %s alg %d dtype %d save_mode %d",
                   sys->name.c_str(), o->alg, o->dtype, o->save_mode);
@@ -581,7 +588,11 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
   a.n_steps = adaptive ? 0 : o->n_steps;
   a.n_save = o->save_mode == SDE_SAVE_SAVEAT ? (int)o->n_save : 0;
   // the kernels only look at kCompatRuntimeZero (bit 30), which must reach them as 0; the variants were chosen by get_kernel
-  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS);
+  a.compat = o->compat & (SDE_COMPAT_FIX_VERN9_INTERP | SDE_COMPAT_STRICT_CONTROLLER | SDE_COMPAT_LOG2_CONTROLLER | SDE_COMPAT_FAST_RHS | SDE_COMPAT_FAST_STAGES);
+  if (want_fast_stages(o)) {     // h_ij = dt * a_ij in the state's precision, like the product the reference-exact kernels form for a21
+    static_assert(sde_host::kTsit5NStageCoef == (int)(sizeof(a.hcoef) / sizeof(a.hcoef[0])), "stage coefficients");
+    for (int k = 0; k < sde_host::kTsit5NStageCoef; ++k) a.hcoef[k] = (T)((T)o->dt * (T)sde_host::kTsit5StageCoef[k]);
+  }
   a.layout = o->layout;
   a.max_attempts = o->max_attempts;
   a.out_u = (T*)d_out_u;

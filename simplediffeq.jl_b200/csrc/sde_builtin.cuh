@@ -38,8 +38,9 @@ inline KernelInfo pick_fixed(bool staged) {
 }
 
 template <class Sys, class T>
-inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool staged) {
+inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool staged, bool fast_stages) {
   using TS = Tsit5Method<Sys, T>;
+  using TF = Tsit5FastMethod<Sys, T>;     // SDE_COMPAT_FAST_STAGES: the step size folded into the stage coefficients
   using RK = RK4Method<Sys, T>;
   using EU = EulerMethod<Sys, T>;
   using V7 = Vern7Method<Sys, T>;
@@ -50,7 +51,10 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool 
           : KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, false>, true})
   switch (alg) {
     case kTsit5:
-      if (save == kSaveEndpoint) return SDE_FIXED(TS, kSaveEndpoint, false);
+      // (SDE_COMPAT_FAST_STAGES applies to the endpoint-only kernel; series outputs keep the reference-order stages: the
+      //  21 folded coefficients cost 42 registers, which the store-bound kernels need for occupancy -- the saveat
+      //  kernel would go from 96 to 148)
+      if (save == kSaveEndpoint) return fast_stages ? SDE_FIXED(TF, kSaveEndpoint, false) : SDE_FIXED(TS, kSaveEndpoint, false);
       if (save == kSaveAt) return SDE_FIXED(TS, kSaveAt, false);
       if (save == kSaveEveryStep) return SDE_FIXED(TS, kSaveEveryStep, false);
       break;
@@ -95,9 +99,9 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool 
 
 template <class Sys>
 inline KernelInfo lookup_kernel(int alg, int dtype, int save, int variant) {
-  const bool q2 = (variant & 1) != 0, strict = (variant & 2) != 0, staged = (variant & 4) != 0;
-  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2, strict, staged)
-                    : lookup_kernel_t<Sys, float>(alg, save, q2, strict, staged);
+  const bool q2 = (variant & 1) != 0, strict = (variant & 2) != 0, staged = (variant & 4) != 0, fast_stages = (variant & 8) != 0;
+  return dtype == 0 ? lookup_kernel_t<Sys, double>(alg, save, q2, strict, staged, fast_stages)
+                    : lookup_kernel_t<Sys, float>(alg, save, q2, strict, staged, fast_stages);
 }
 
 }  // namespace sde

@@ -152,6 +152,8 @@ sde::KArgs<T> make_args(const Call& c, sde::u64* queue) {
   a.out_u = (T*)c.out_u; a.ld_out = c.n_traj; a.n_out = c.n_out; a.out_t = (T*)c.out_t;
   a.naccept = c.naccept; a.nreject = c.nreject; a.retcode = c.retcode;
   a.queue = queue;
+  // like the launcher (sde_api.cu) for SDE_COMPAT_FAST_STAGES: h_ij = dt * a_ij
+  for (int k = 0; k < sde_host::kTsit5NStageCoef; ++k) a.hcoef[k] = (T)((T)c.dt * (T)sde_host::kTsit5StageCoef[k]);
   return a;
 }
 
@@ -279,6 +281,21 @@ extern "C" int emul_solve(int sys, int alg, int dtype, int save, int layout, int
   Call c{alg, save, compat, layout, n_traj, n_steps, n_save, n_out, max_attempts, t0, tf, dt, abstol, reltol,
          u0, p, tgrid, saveat, out_u, out_t, naccept, nreject, retcode};
   return dtype == 0 ? dispatch_sys<double>(sys, c) : dispatch_sys<float>(sys, c);
+}
+
+// ---- SDE_COMPAT_FAST_RHS, fixed-step Tsit5, endpoint only: the contracted right-hand-side twins with the step size folded
+// into the stage coefficients (sde_kernels.cuh: Tsit5FastMethod) -- the kernels sde_builtin.cuh instantiates for them.
+// sys: 0 = lorenz twin, 1 = vanderpol twin
+extern "C" int emul_fast_tsit5(int sys, int dtype, long long n_traj, const void* u0, const void* p, double t0, double dt,
+                               long long n_steps, const void* tgrid, void* out_u) {
+  Call c{sde::kTsit5, sde::kSaveEndpoint, 0, 0, n_traj, n_steps, 0, 1, 0, t0, 0.0, dt, 0.0, 0.0,
+         u0, p, tgrid, nullptr, out_u, nullptr, nullptr, nullptr, nullptr};
+  if (sys == 0 && dtype == 0) run_fixed<sde::LorenzFma, double, sde::Tsit5FastMethod<sde::LorenzFma, double>, sde::kSaveEndpoint>(c);
+  else if (sys == 0) run_fixed<sde::LorenzFma, float, sde::Tsit5FastMethod<sde::LorenzFma, float>, sde::kSaveEndpoint>(c);
+  else if (sys == 1 && dtype == 0) run_fixed<sde::VanDerPolFma, double, sde::Tsit5FastMethod<sde::VanDerPolFma, double>, sde::kSaveEndpoint>(c);
+  else if (sys == 1) run_fixed<sde::VanDerPolFma, float, sde::Tsit5FastMethod<sde::VanDerPolFma, float>, sde::kSaveEndpoint>(c);
+  else return -1;
+  return 0;
 }
 
 // ---- SimpleEM (csrc/device/sde_em.cuh: em_body, Philox4x32-10 + Box-Muller) ---------------------------------------

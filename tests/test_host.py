@@ -92,6 +92,7 @@ def test_header_ids_match_python_ids(sde):
     assert ids["SDE_COMPAT_STRICT_CONTROLLER"] == _lib.COMPAT_STRICT_CONTROLLER
     assert ids["SDE_COMPAT_LOG2_CONTROLLER"] == _lib.COMPAT_LOG2_CONTROLLER
     assert ids["SDE_COMPAT_FAST_RHS"] == _lib.COMPAT_FAST_RHS
+    assert ids["SDE_COMPAT_FAST_STAGES"] == _lib.COMPAT_FAST_STAGES
     assert ctypes.sizeof(_lib.SdeOptions) == 6 * 4 + 8 + 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8
 
 
@@ -140,7 +141,7 @@ def test_option_validation_errors(sde):
     assert L.sde_system_prepare(None, ctypes.byref(o)) == -1
     o.dtype = 0
     assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == 0
-    for bad in (16, 0x40000000, 2 | 4):   # unknown compat bits (bit 30 must reach the kernels as 0: sde::late_flag);
+    for bad in (32, 0x40000000, 2 | 4):   # unknown compat bits (bit 30 must reach the kernels as 0: sde::late_flag);
                                          # literal and log2-domain controller forced at the same time
         o.compat = bad
         assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == -1

@@ -149,6 +149,8 @@ def test_constants_agree_with_the_header():
     assert [int(x) for x in m.groups()] == [enum["SDE_COMPAT_FIX_VERN9_INTERP"], enum["SDE_COMPAT_STRICT_CONTROLLER"], enum["SDE_COMPAT_LOG2_CONTROLLER"]]
     m = re.search(r"const SDE_COMPAT_FAST_RHS = Int32\((\d)\)", SHIM)
     assert int(m.group(1)) == enum["SDE_COMPAT_FAST_RHS"]
+    m = re.search(r"const SDE_COMPAT_FAST_STAGES = Int32\((\d+)\)", SHIM)
+    assert int(m.group(1)) == enum["SDE_COMPAT_FAST_STAGES"]
     assert enum["SDE_RET_DTMIN"] == 1 and "any(==(1), ret) && error(\"dt<dtmin\")" in SHIM
     # the python mirror and the shim construct the option struct with the same number of fields
     n_args = len(_split_top(re.search(r"SdeOptions\((alg_id\(alg\).*?capacity)\)\)", SHIM, flags=re.S).group(1)))

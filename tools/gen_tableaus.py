@@ -411,6 +411,15 @@ def emit_host_interp(ts, v, specs):
             o.append("  {" + ", ".join(lit(x) for x in row) + "},\n")
         o.append("};\n")
         o.append("static const int k%sLen[%d] = {%s};\n\n" % (name, len(sp["polys"]), ", ".join(str(len(c)) for _, c in sp["polys"])))
+    # SDE_COMPAT_FAST_STAGES (sde_kernels.cuh: Tsit5FastMethod): the launcher folds the step size into these
+    names = ["a%d%d" % (s, j) for s in range(2, 8) for j in range(1, s)]
+    o.append("// Tsit5 stage coefficients a21, a31, a32, ... a76 (row by row): the launcher hands dt * a_ij to the\n"
+             "// SDE_COMPAT_FAST_STAGES kernels through KArgs::hcoef\n")
+    o.append("static const int kTsit5NStageCoef = %d;\n" % len(names))
+    o.append("static const double kTsit5StageCoef[%d] = {\n" % len(names))
+    for nm in names:
+        o.append("  /*%s*/ %s,\n" % (nm, lit(vals["Tsit5"][nm])))
+    o.append("};\n\n")
     o.append("}  // namespace sde_host\n")
     return "".join(o)
 
