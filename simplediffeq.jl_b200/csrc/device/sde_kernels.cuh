@@ -93,12 +93,12 @@ struct EulerMethod {
 };
 
 // ------------------------------------------------------------------------------------------
-// SDE_COMPAT_FAST_RHS, fixed-step Tsit5: the stage sums with the step size folded into the coefficients,
+// SDE_COMPAT_FAST_STAGES, fixed-step Tsit5 keeping only the last state: the stage sums with the step size folded into the coefficients,
 //     tmp = uprev + sum_j (dt * a_ij) * k_j        instead of the reference's   uprev + dt * (sum_j a_ij * k_j)
 // -- h_ij = dt * a_ij is the same for every step and every trajectory of a fixed-step launch, so a stage costs one
 // FMA per nonzero coefficient: 21 N instead of 26 N + 1 FP64 instructions per step (Lorenz with its contracted
-// right-hand side: 115 -> 99).  NOT the reference's arithmetic (one rounding per term moves); the flag's documented
-// deviation applies.  Dense output and FSAL handling are the base method's.
+// right-hand side, SDE_COMPAT_FAST_RHS: 115 -> 99).  NOT the reference's arithmetic: every term is rounded at the magnitude of
+// the state; the flag's documented deviation applies (simplediffeq_cuda.h).  Dense output and FSAL handling are the base method's.
 // ------------------------------------------------------------------------------------------
 template <class Sys, class T>
 struct Tsit5FastMethod : Tsit5Method<Sys, T> {

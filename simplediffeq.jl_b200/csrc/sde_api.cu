@@ -704,6 +704,157 @@ struct RangeSource {
   int64_t max_piece() const { return shared ? std::min(total, guided_len(0)) : hi - lo; }
 };
 
+// --------------------------------------------------------------------------------------------
+// Small host-buffer solves (config 1 of BASELINE.json: 10 k trajectories, a 0.59 ms kernel).  The general path below
+// costs ~30 runtime calls per solve -- a stream, seven stream-ordered allocations, two pitched H2D copies, up to six D2H
+// copies into pageable memory (each one a synchronisation), the frees, the pool trim: 0.25 ms around that kernel
+// (tools/small_solve_overhead.py).  A solve whose inputs and outputs fit kSmallSolveBytes instead borrows a cached
+// context -- one stream, one device buffer, one pinned staging buffer -- packs its inputs into the staging buffer,
+// and runs ONE H2D copy, the kernel and ONE D2H copy on that stream; the outputs are scattered to the caller's arrays
+// by the host.  Contexts are pooled (any thread, one user at a time) and released by sde_trim().
+// --------------------------------------------------------------------------------------------
+constexpr size_t kSmallSolveBytes = (size_t)4 << 20;
+struct SmallCtx {
+  int dev = -1;
+  cudaStream_t st = nullptr;
+  char* d = nullptr;       // device buffer
+  char* h = nullptr;       // pinned host staging, same layout
+  size_t cap = 0;
+};
+std::mutex g_small_mu;
+std::vector<SmallCtx*> g_small_free;
+
+void small_destroy(SmallCtx* c) {
+  if (c->d) cudaFree(c->d);
+  if (c->h) cudaFreeHost(c->h);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+// a context of the current device with at least `bytes` of device and staging memory
+int small_acquire(int dev, size_t bytes, SmallCtx** out) {
+  SmallCtx* c = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    for (size_t i = 0; i < g_small_free.size(); ++i)
+      if (g_small_free[i]->dev == dev) { c = g_small_free[i]; g_small_free.erase(g_small_free.begin() + (long)i); break; }
+  }
+  if (!c) { c = new SmallCtx; c->dev = dev; }
+  cudaError_t e = cudaSuccess;
+  if (!c->st) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess && c->cap < bytes) {
+    if (c->d) { cudaFree(c->d); c->d = nullptr; }
+    if (c->h) { cudaFreeHost(c->h); c->h = nullptr; }
+    c->cap = 0;
+    const size_t cap = std::max<size_t>((bytes + 0xfffff) & ~(size_t)0xfffff, (size_t)1 << 20);
+    e = cudaMalloc((void**)&c->d, cap);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h, cap, cudaHostAllocDefault);
+    if (e == cudaSuccess) c->cap = cap;
+  }
+  if (e != cudaSuccess) {
+    small_destroy(c);
+    return fail(SDE_ERR_CUDA, "small-solve context: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return SDE_OK;
+}
+void small_release(SmallCtx* c) {
+  std::lock_guard<std::mutex> lk(g_small_mu);
+  g_small_free.push_back(c);
+}
+void small_trim() {
+  std::vector<SmallCtx*> all;
+  {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    all.swap(g_small_free);
+  }
+  for (SmallCtx* c : all) small_destroy(c);
+}
+
+// trajectories [c0, c1) of a host-buffer solve on the current device through a cached context (see above)
+int small_solve(sde_system_s* sys, const sde_options_t* o, const void* fn, int dev, int64_t c0, int64_t c1,
+                const char* u0, const char* p, char* out_u, char* out_t, int32_t* nacc, int32_t* nrej, int32_t* ret,
+                bool trace) {
+  const size_t es = esize(o->dtype);
+  const int N = sys->n_state, NP = sys->n_param;
+  const int64_t n_all = o->n_traj, n = c1 - c0, slots = out_slots(o);
+  const bool series = o->save_mode != SDE_SAVE_ENDPOINT;
+  const bool adaptive = is_adaptive(o->alg);
+  const bool t_series = adaptive && o->save_mode == SDE_SAVE_EVERYSTEP;
+  const bool tm = o->layout == SDE_LAYOUT_TRAJ_MAJOR;
+  const int64_t ld = (n + 31) & ~(int64_t)31;         // device pitch of the SoA rows, in elements
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off += up(bytes); return at; };
+  const size_t o_u0 = take(es * N * ld), o_p = take(es * NP * ld);
+  const size_t in_bytes = off;
+  const size_t o_out = take(es * N * slots * ld);
+  const size_t o_t = (adaptive && out_t) ? take(es * (t_series ? slots : 1) * ld) : 0;
+  const size_t o_na = nacc ? take(4 * ld) : 0, o_nr = nrej ? take(4 * ld) : 0, o_rc = ret ? take(4 * ld) : 0;
+  const size_t out_bytes = off - in_bytes;
+  const size_t o_q = take(16 * kQueueSlots);          // work-queue heads (adaptive kernels)
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(now() - a).count(); };
+  auto t_phase = now();
+  SmallCtx* c = nullptr;
+  int rc = small_acquire(dev, off, &c);
+  if (rc != SDE_OK) return rc;
+  cudaStream_t st = c->st;
+  SolveConsts consts;
+  bool consts_owned = false;
+  auto finish = [&](int code) {       // nothing in flight may still use the context when it goes back to the pool
+    cudaStreamSynchronize(st);
+    small_release(c);
+    return code;
+  };
+#define SDE_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+      return finish(fail(SDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+  // inputs: SoA rows of the range, packed with the device pitch
+  for (int r = 0; r < N; ++r) memcpy(c->h + o_u0 + es * r * ld, u0 + es * ((size_t)r * n_all + c0), es * n);
+  for (int r = 0; r < NP; ++r) memcpy(c->h + o_p + es * r * ld, p + es * ((size_t)r * n_all + c0), es * n);
+  SDE_TRY(cudaMemcpyAsync(c->d, c->h, in_bytes, cudaMemcpyHostToDevice, st));
+  // constants: adaptive solves without saveat need only the queue heads, which live in the context's buffer
+  if (adaptive && o->save_mode != SDE_SAVE_SAVEAT) {
+    consts.scratch = c->d + o_q;
+  } else {
+    cudaMemPool_t pool;
+    rc = device_pool(dev, &pool);
+    if (rc == SDE_OK) rc = upload_consts(o, pool, st, &consts);
+    if (rc != SDE_OK) return finish(rc);
+    consts_owned = true;
+  }
+  sde_options_t oc = *o;
+  oc.n_traj = n;
+  rc = launch_piece(sys, &oc, fn, consts, 0, c->d + o_u0, c->d + o_p, ld, c->d + o_out, ld,
+                    (adaptive && out_t) ? c->d + o_t : nullptr, nacc ? (int32_t*)(c->d + o_na) : nullptr,
+                    nrej ? (int32_t*)(c->d + o_nr) : nullptr, ret ? (int32_t*)(c->d + o_rc) : nullptr, st);
+  if (consts_owned && consts.scratch) cudaFreeAsync(consts.scratch, st);      // stream-ordered: after the kernel
+  if (rc != SDE_OK) return finish(rc);
+  SDE_TRY(cudaMemcpyAsync(c->h + in_bytes, c->d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, st));
+  SDE_TRY(cudaStreamSynchronize(st));
+#undef SDE_TRY
+  if (trace) { fprintf(stderr, "[sde trace] dev %d: [%lld,%lld) small solve, device part %.3f ms\n", dev, (long long)c0, (long long)c1, ms_since(t_phase)); t_phase = now(); }
+  // outputs back to the caller's layout (the same index arithmetic as the D2H copies of the general path)
+  const char* h = c->h;
+  if (!series) {
+    for (int r = 0; r < N; ++r) memcpy(out_u + es * ((size_t)r * n_all + c0), h + o_out + es * r * ld, es * n);
+  } else if (tm) {
+    memcpy(out_u + es * N * slots * c0, h + o_out, es * N * slots * n);
+  } else {
+    for (int64_t r = 0; r < (int64_t)N * slots; ++r) memcpy(out_u + es * ((size_t)r * n_all + c0), h + o_out + es * r * ld, es * n);
+  }
+  if (adaptive && out_t) {
+    if (!t_series) memcpy(out_t + es * c0, h + o_t, es * n);
+    else if (tm) memcpy(out_t + es * slots * c0, h + o_t, es * slots * n);
+    else for (int64_t r = 0; r < slots; ++r) memcpy(out_t + es * ((size_t)r * n_all + c0), h + o_t + es * r * ld, es * n);
+  }
+  if (nacc) memcpy(nacc + c0, h + o_na, 4 * n);
+  if (nrej) memcpy(nrej + c0, h + o_nr, 4 * n);
+  if (ret) memcpy(ret + c0, h + o_rc, 4 * n);
+  small_release(c);
+  if (trace) fprintf(stderr, "[sde trace] dev %d: small solve, scatter + release %.3f ms\n", dev, ms_since(t_phase));
+  return SDE_OK;
+}
+
 // one device of a host-buffer solve.
 // The device's range is cut into pieces; piece i uses buffer set i % 2 on stream i % 2, each stream
 // running H2D -> kernel -> D2H in order, so the copies of one piece overlap the kernel of its
@@ -774,6 +925,14 @@ int solve_shard(sde_system_s* sys, const sde_options_t* o, int device, RangeSour
     if (piece > 32) piece = (piece + 31) & ~(int64_t)31;
     int n_buf = piece >= range ? 1 : kBuf;
     if (const char* e = getenv("SDE_TUNE_NBUF")) n_buf = std::max(1, std::min(kBuf, atoi(e)));   // measurement only
+
+    // small solves: one cached context, one copy each way (small_solve above); SDE_TUNE_NO_SMALL = measurement only
+    if (!src.shared && n_buf == 1 && piece >= range && range > 0 && !getenv("SDE_TUNE_NO_SMALL") && !getenv("SDE_TUNE_PIECE") &&
+        per_traj * (size_t)range <= kSmallSolveBytes) {
+      int64_t c0 = 0, c1 = 0;
+      src.next(range, &c0, &c1);
+      return small_solve(sys, o, fn, dev, c0, c1, u0, p, out_u, out_t, nacc, nrej, ret, trace);
+    }
 
     cudaStream_t st[kBuf] = {nullptr, nullptr};
     Buffers buf[kBuf];
@@ -1057,6 +1216,7 @@ int sde_host_free(void* ptr) {
 int64_t sde_launch_count(void) { return g_launches.load(); }
 
 int sde_trim(void) {
+  small_trim();
   std::lock_guard<std::mutex> lk(g_pool_mu);
   for (auto& kv : g_pools) {
     cudaError_t e = cudaMemPoolTrimTo(kv.second, 0);
