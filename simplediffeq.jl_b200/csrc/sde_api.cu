@@ -623,6 +623,16 @@ int launch_piece_t(sde_system_s* sys, const sde_options_t* o, const void* fn, co
     SDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem));
     if (per_sm < 1) per_sm = 1;
+    // Ensembles of about as many trajectories as there are resident lanes: with one trajectory per lane a warp issues
+    // until its longest lane is done, while lanes that take a second trajectory from the queue even the warps out.
+    // Aim at two trajectories per lane, but keep at least three CTAs per SM for latency hiding (B200, 2^16 / 2^17
+    // trajectories: -4 ... -20 % time on sorted and shuffled Van der Pol / Lorenz sweeps, neutral from 2^18 on, where a
+    // smaller grid helps shuffled sweeps and hurts sorted ones: profiles/r2_cta_cap_probe.txt).
+    {
+      const int64_t two_per_lane = (o->n_traj + (int64_t)sms * kBlock * 2 - 1) / ((int64_t)sms * kBlock * 2);
+      per_sm = (int)std::min<int64_t>(per_sm, std::max<int64_t>(3, two_per_lane));
+    }
+    if (const char* e = getenv("SDE_TUNE_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // measurement only
     grid = (unsigned)std::min<int64_t>(full, (int64_t)sms * per_sm);   // persistent CTAs
   } else {
     if (full > 0x7fffffffLL) return fail(SDE_ERR_INVALID, "n_traj too large for one launch");
@@ -812,6 +822,9 @@ int small_solve(sde_system_s* sys, const sde_options_t* o, const void* fn, int d
   for (int r = 0; r < N; ++r) memcpy(c->h + o_u0 + es * r * ld, u0 + es * ((size_t)r * n_all + c0), es * n);
   for (int r = 0; r < NP; ++r) memcpy(c->h + o_p + es * r * ld, p + es * ((size_t)r * n_all + c0), es * n);
   SDE_TRY(cudaMemcpyAsync(c->d, c->h, in_bytes, cudaMemcpyHostToDevice, st));
+  // the one D2H copy below also moves the padding between the output arrays (row pitch, 256-byte alignment), which no
+  // kernel writes: defined bytes instead of whatever the buffer held (compute-sanitizer initcheck reads them as uninitialised)
+  SDE_TRY(cudaMemsetAsync(c->d + in_bytes, 0, out_bytes, st));
   // constants: adaptive solves without saveat need only the queue heads, which live in the context's buffer
   if (adaptive && o->save_mode != SDE_SAVE_SAVEAT) {
     consts.scratch = c->d + o_q;
