@@ -123,7 +123,7 @@ enum {
                                        bifurcation at rho = 13.926 (max 6e-12); unbounded for chaotic trajectories,
                                        like any rounding change.  Off by default. */
   SDE_COMPAT_FAST_STAGES = 16       /* throughput beyond the reference-exact ceiling, second step: fixed-step
-                                       GPUSimpleTsit5 keeping only the last state (save_mode ENDPOINT) folds the step
+                                       GPUSimpleTsit5 (every save mode) folds the step
                                        size into the stage coefficients, tmp = uprev + sum_j (dt a_ij) k_j instead
                                        of the reference's uprev + dt (sum_j a_ij k_j): 21 N instead of 26 N + 1 FP64
                                        instructions per step for the stage sums, any system (built-in or CUDA-C).
@@ -132,8 +132,9 @@ enum {
                                        rounded at the magnitude of the state, so the deviation from the reference
                                        is that of one more rounding of u per stage: on BASELINE config 2's sweep
                                        median 5e-15 relative, 99.9 % of the trajectories <= 6e-13, <= 1e-12 except
-                                       within 0.025 of rho = 13.926 (max 2.3e-11).  Other algorithms and save modes
-                                       ignore the flag.  Off by default. */
+                                       within 0.025 of rho = 13.926 (max 2.3e-11).  Dense output (saveat) is the
+                                       reference's formula on the deviating stages.  Other algorithms ignore the
+                                       flag.  Off by default. */
 };
 
 typedef struct sde_system_s* sde_system_t;

@@ -93,7 +93,7 @@ struct EulerMethod {
 };
 
 // ------------------------------------------------------------------------------------------
-// SDE_COMPAT_FAST_STAGES, fixed-step Tsit5 keeping only the last state: the stage sums with the step size folded into the coefficients,
+// SDE_COMPAT_FAST_STAGES, fixed-step Tsit5: the stage sums with the step size folded into the coefficients,
 //     tmp = uprev + sum_j (dt * a_ij) * k_j        instead of the reference's   uprev + dt * (sum_j a_ij * k_j)
 // -- h_ij = dt * a_ij is the same for every step and every trajectory of a fixed-step launch, so a stage costs one
 // FMA per nonzero coefficient: 21 N instead of 26 N + 1 FP64 instructions per step (Lorenz with its contracted

@@ -103,9 +103,9 @@ bool want_strict(const sde_options_t* o) {
   if (o->compat & SDE_COMPAT_LOG2_CONTROLLER) return false;
   return o->dtype == SDE_F32 || o->reltol <= 1e-11;
 }
-// SDE_COMPAT_FAST_STAGES acts on the fixed-step Tsit5 kernel that keeps only the last state (Tsit5FastMethod)
+// SDE_COMPAT_FAST_STAGES acts on the fixed-step Tsit5 kernels (Tsit5FastMethod), whatever they save
 bool want_fast_stages(const sde_options_t* o) {
-  return (o->compat & SDE_COMPAT_FAST_STAGES) && o->alg == SDE_ALG_TSIT5 && o->save_mode == SDE_SAVE_ENDPOINT;
+  return (o->compat & SDE_COMPAT_FAST_STAGES) && o->alg == SDE_ALG_TSIT5;
 }
 bool want_staged(const sde_options_t* o) {
   return !is_adaptive(o->alg) && o->save_mode != SDE_SAVE_ENDPOINT && o->layout == SDE_LAYOUT_TRAJ_MAJOR;
@@ -242,8 +242,8 @@ std::string user_program(const sde_system_s* sys, int alg, int dtype, int save, 
              "extern \"C\" __global__ void __launch_bounds__(%d, %d) sde_user_kernel(const __grid_constant__ sde::KArgs<real> a) {\n"
              "  sde::fixed_body<SdeUserSys, real, %s<SdeUserSys, real>, %d, %s, %s>(a);\n}\n",
              kBlock, tune_min_blocks() > 0 ? tune_min_blocks() : ((staged && !(((alg == SDE_ALG_VERN7 || alg == SDE_ALG_VERN9) && dtype == SDE_F64) || sys->n_state > 4)) ? 4 : 1),
-             // SDE_COMPAT_FAST_STAGES, fixed-step Tsit5, endpoint only: step size folded into the stage coefficients
-             (fast_stages && alg == SDE_ALG_TSIT5 && save == SDE_SAVE_ENDPOINT) ? "sde::Tsit5FastMethod" : method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
+             // SDE_COMPAT_FAST_STAGES, fixed-step Tsit5: step size folded into the stage coefficients
+             (fast_stages && alg == SDE_ALG_TSIT5) ? "sde::Tsit5FastMethod" : method_name(alg), save, q2 ? "true" : "false", staged ? "true" : "false");
   }
   s += buf;
   return s;

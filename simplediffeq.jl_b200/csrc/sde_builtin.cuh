@@ -51,12 +51,9 @@ inline KernelInfo lookup_kernel_t(int alg, int save, bool q2, bool strict, bool 
           : KernelInfo{(const void*)&adaptive_kernel<Sys, T, M, S, V, false>, true})
   switch (alg) {
     case kTsit5:
-      // (SDE_COMPAT_FAST_STAGES applies to the endpoint-only kernel; series outputs keep the reference-order stages: the
-      //  21 folded coefficients cost 42 registers, which the store-bound kernels need for occupancy -- the saveat
-      //  kernel would go from 96 to 148)
       if (save == kSaveEndpoint) return fast_stages ? SDE_FIXED(TF, kSaveEndpoint, false) : SDE_FIXED(TS, kSaveEndpoint, false);
-      if (save == kSaveAt) return SDE_FIXED(TS, kSaveAt, false);
-      if (save == kSaveEveryStep) return SDE_FIXED(TS, kSaveEveryStep, false);
+      if (save == kSaveAt) return fast_stages ? SDE_FIXED(TF, kSaveAt, false) : SDE_FIXED(TS, kSaveAt, false);
+      if (save == kSaveEveryStep) return fast_stages ? SDE_FIXED(TF, kSaveEveryStep, false) : SDE_FIXED(TS, kSaveEveryStep, false);
       break;
     case kRK4:   // the reference's GPUSimpleRK4 has no saveat
       if (save == kSaveEndpoint) return SDE_FIXED(RK, kSaveEndpoint, false);
