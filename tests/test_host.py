@@ -125,6 +125,11 @@ def test_every_builtin_kernel_exists(sde):
                     unsupported = isinstance(alg, (sde.GPUSimpleRK4, sde.GPUSimpleEuler)) and mode == 1
                     assert (rc == -4) if unsupported else (rc == 0), (name, alg, dtype, mode, L.sde_last_error())
                     n_ok += rc == 0
+                    if rc == 0:     # every variant the compat flags select is in the build too (layouts / fast flags / Q2 fix)
+                        for compat, layout in ((_lib.COMPAT_FAST_RHS | _lib.COMPAT_FAST_STAGES, 0), (_lib.COMPAT_FAST_STAGES, 1),
+                                               (_lib.COMPAT_FIX_VERN9_INTERP, 1)):
+                            o.compat, o.layout = compat, layout
+                            assert L.sde_system_prepare(sysm._handle, ctypes.byref(o)) == 0, (name, alg, dtype, mode, compat, layout)
     assert n_ok == 7 * 2 * (3 + 3 + 2 + 3 + 3 + 3 + 3 + 2)
 
 
@@ -141,6 +146,9 @@ def test_option_validation_errors(sde):
     assert L.sde_system_prepare(None, ctypes.byref(o)) == -1
     o.dtype = 0
     assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == 0
+    for good in (_lib.COMPAT_FAST_RHS, _lib.COMPAT_FAST_STAGES, _lib.COMPAT_FAST_RHS | _lib.COMPAT_FAST_STAGES | _lib.COMPAT_FIX_VERN9_INTERP):
+        o.compat = good                   # the opt-in fast flags combine freely with each other and with the others
+        assert L.sde_system_prepare(sde.systems.lorenz._handle, ctypes.byref(o)) == 0
     for bad in (32, 0x40000000, 2 | 4):   # unknown compat bits (bit 30 must reach the kernels as 0: sde::late_flag);
                                          # literal and log2-domain controller forced at the same time
         o.compat = bad
