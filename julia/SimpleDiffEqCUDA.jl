@@ -207,7 +207,8 @@ end
 
 # ==================================================================================================
 # SimpleEM: solve(EnsembleProblem(SDEProblem(f, g, u0, tspan, p); prob_func), SimpleEM(), EnsembleCUDAB200();
-#                 trajectories, dt, seed = 0)                 (replaces src/euler_maruyama.jl:48-94 per trajectory)
+#                 trajectories, dt, seed = rand(UInt64))      (replaces src/euler_maruyama.jl:48-94 per trajectory;
+#                 a fresh Philox key per solve like the reference's randn, an explicit seed reproduces a run)
 # ==================================================================================================
 struct SdeEmOptions
     dtype::Int32
@@ -252,7 +253,7 @@ const DEVICE_SDE = IdDict{Any, DeviceSDE}()
 register_device_sde!(f, sde::DeviceSDE) = (DEVICE_SDE[f] = sde)
 
 function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::SimpleEM, ensemblealg::EnsembleCUDAB200;
-        trajectories, dt = error("dt required for SimpleEM"), seed::Integer = 0, kwargs...)
+        trajectories, dt = error("dt required for SimpleEM"), seed::Integer = rand(UInt64), kwargs...)
     prob = ensembleprob.prob
     @assert !SciMLBase.isinplace(prob)
     T = eltype(prob.u0)
@@ -273,7 +274,7 @@ function SciMLBase.__solve(ensembleprob::EnsembleProblem, alg::SimpleEM, ensembl
     nst = Int((T(prob.tspan[2]) - t0) / dtT)                 # n - 1; InexactError as in the reference (:66)
     out_u = Array{T}(undef, N, nst + 1, n)                    # trajectory major, every state (:67)
     opt = Ref(SdeEmOptions(T === Float64 ? 0 : 1, SDE_SAVE_EVERYSTEP, SDE_LAYOUT_TRAJ_MAJOR, 0, n, t0, dtT, nst,
-        UInt64(seed), 0))
+        seed % UInt64, 0))
     check(ccall((:sde_em_solve, libsde), Cint,
         (Ptr{Cvoid}, Ref{SdeEmOptions}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cint),
         sde.handle, opt, u0, p, C_NULL, out_u, ensemblealg.devices, length(ensemblealg.devices)))
