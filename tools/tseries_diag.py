@@ -1,3 +1,5 @@
+"""Development aid (cited by tests/test_gpu_parity.py::test_adaptive_everystep_variable_length): how far the time series of an adaptive
+every-step solve moves when `pow` differs by one ulp -- the oracle against its own 1-ulp-pow twin and against the GPU."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
