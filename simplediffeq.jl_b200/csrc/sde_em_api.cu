@@ -260,10 +260,15 @@ int em_solve_shard(sde_em_system_s* sys, const sde_em_options_t* o, int device, 
     cudaMemPool_t pool;
     rc = device_pool(dev, &pool);
     if (rc != SDE_OK) return rc;
-    size_t free_b = 0, total_b = 0;
-    SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t per_traj = es * ((size_t)N + NP + (size_t)N * slots + (provided ? (size_t)n_normals : 0));
-    int64_t piece = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
+    int64_t piece = hi - lo;
+    // large solves: pieces bounded by what is free now (cudaMemGetInfo costs ~0.3 ms, so small solves skip it like
+    // sde_solve does: any B200 has 512 MB to spare; SDE_TUNE_EM_MEMINFO = measurement only)
+    if ((double)per_traj * (double)(hi - lo) > 512.0 * 1048576.0 || getenv("SDE_TUNE_EM_MEMINFO")) {
+      size_t free_b = 0, total_b = 0;
+      SDE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      piece = (int64_t)std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_traj);
+    }
     if (const char* e = getenv("SDE_TUNE_PIECE")) piece = std::max<int64_t>(32, atoll(e));   // measurement / tests only
     piece = std::min<int64_t>(piece, hi - lo);
     if (piece > 32) piece = (piece + 31) & ~(int64_t)31;
