@@ -23,6 +23,10 @@ for name in ("vanderpol", "scalargrowth"):
         S.solve_arrays(getattr(S.systems, name), S.GPUSimpleTsit5(), np.ascontiguousarray(a0.T), np.ascontiguousarray(b0.T), (0.0, 1.0),
                        dt=0.0625, saveat=S.jl_range(dt_(0.0), dt_(0.0025), dt_(1.0), dt_), save_mode=1, layout=0)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleRK4(), u0s, ps, (0.0, 1.0), dt=0.002, save_mode=2, layout=0)               # 501 slots per row
+# opt-in fast kernels (SDE_COMPAT_FAST_RHS | SDE_COMPAT_FAST_STAGES: stage coefficients through the kernel parameters), every save mode
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, compat=24)
+S.solve_arrays(S.systems.lorenz, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, saveat=sa, save_mode=1, layout=0, compat=24)
+S.solve_arrays(S.systems.robertson, S.GPUSimpleTsit5(), u0s, ps, (0.0, 1.0), dt=0.01, save_mode=2, layout=1, compat=16)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7)           # work queue
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleAVern9(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-9, reltol=1e-9, saveat=sa, save_mode=1, layout=1)
 S.solve_arrays(S.systems.lorenz, S.GPUSimpleATsit5(), u0s, ps, (0.0, 1.0), dt=0.1, abstol=1e-7, reltol=1e-7, save_mode=2, out_capacity=64)
