@@ -123,18 +123,19 @@ enum {
                                        bifurcation at rho = 13.926 (max 6e-12); unbounded for chaotic trajectories,
                                        like any rounding change.  Off by default. */
   SDE_COMPAT_FAST_STAGES = 16       /* throughput beyond the reference-exact ceiling, second step: fixed-step
-                                       GPUSimpleTsit5 (every save mode) folds the step
-                                       size into the stage coefficients, tmp = uprev + sum_j (dt a_ij) k_j instead
-                                       of the reference's uprev + dt (sum_j a_ij k_j): 21 N instead of 26 N + 1 FP64
-                                       instructions per step for the stage sums, any system (built-in or CUDA-C).
-                                       With SDE_COMPAT_FAST_RHS on lorenz: 126 -> 99 per step,
-                                       1.84e11 steps/s on BASELINE config 2 (+25 % over the reference-exact kernel).  Every term is then
-                                       rounded at the magnitude of the state, so the deviation from the reference
-                                       is that of one more rounding of u per stage: on BASELINE config 2's sweep
-                                       median 5e-15 relative, 99.9 % of the trajectories <= 6e-13, <= 1e-12 except
-                                       within 0.025 of rho = 13.926 (max 2.3e-11).  Dense output (saveat) is the
-                                       reference's formula on the deviating stages.  Other algorithms ignore the
-                                       flag.  Off by default. */
+                                       GPUSimpleTsit5 (every save mode) folds the step size into the stage
+                                       coefficients, tmp = uprev + sum_j (dt a_ij) k_j instead of the reference's
+                                       uprev + dt (sum_j a_ij k_j): 21 N instead of 26 N + 1 FP64 instructions per
+                                       step for the stage sums, any system (built-in or CUDA-C).  With
+                                       SDE_COMPAT_FAST_RHS on lorenz: 126 -> 99 per step, 1.84e11 steps/s on BASELINE
+                                       config 2 (+25 % over the reference-exact kernel).  Every term is then rounded
+                                       at the magnitude of the state, so the deviation from the reference is that of
+                                       one more rounding of u per stage: on BASELINE config 2's sweep median 5e-15
+                                       relative, 99.9 % of the trajectories <= 6e-13, <= 1e-12 except within 0.025
+                                       of rho = 13.926 (max 2.3e-11).  Dense output (saveat) is the reference's
+                                       formula on the deviating stages.  Helps FP64-bound launches; an HBM-bound
+                                       saveat launch gets a few per cent slower (more registers).  Other algorithms
+                                       ignore the flag.  Off by default. */
 };
 
 typedef struct sde_system_s* sde_system_t;
